@@ -1,0 +1,123 @@
+"""oracle/ — CPU restatement of the reference hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this package.  PARITY UNPINNED (see nnet_oracle.cpp header): the reference has no
+tests or golden vectors and cannot run here (no JVM).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MODES = {"canonical": 0, "relaxed": 1, "random_n": 2, "random_nlogn": 3, "random_logn": 4}
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        src = os.path.join(_HERE, "nnet_oracle.cpp")
+        if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+            build()
+        L = ctypes.CDLL(so)
+        c_dp = ctypes.POINTER(ctypes.c_double)
+        c_ip = ctypes.POINTER(ctypes.c_int32)
+        c_lp = ctypes.POINTER(ctypes.c_int64)
+        L.oracle_order.argtypes = [ctypes.c_int, ctypes.c_int64, c_dp, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, c_ip, c_dp, ctypes.c_int64, c_lp, c_lp]
+        L.oracle_order.restype = ctypes.c_int
+        L.oracle_rowsums.argtypes = [ctypes.c_int64, c_dp, c_dp]
+        L.oracle_setup_d.argtypes = [ctypes.c_int64, c_ip, c_dp, c_dp]
+        L.oracle_unconstrained_ls.argtypes = [ctypes.c_int64, c_dp, c_dp]
+        L.oracle_atx.argtypes = [ctypes.c_int64, c_dp, c_dp]
+        L.oracle_ab.argtypes = [ctypes.c_int64, c_dp, c_dp]
+        L.oracle_split_weights.argtypes = [ctypes.c_int64, c_dp, c_dp, ctypes.c_int, c_lp]
+        L.oracle_java_random.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_ip]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+def _lp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+
+def order(D, mode="canonical", seed=12345, mult=5, additive=False, fallback=1024, want_trace=True):
+    """Returns (ordering[n+1] int32, trace[k,8] float64, counters dict).  D is copied."""
+    n = D.shape[0]
+    Dc = np.array(D, dtype=np.float64, order="C", copy=True)
+    ordering = np.zeros(n + 1, dtype=np.int32)
+    max_trace = n + 8
+    trace = np.zeros((max_trace, 8), dtype=np.float64)
+    ntr = np.zeros(1, dtype=np.int64)
+    cnt = np.zeros(2, dtype=np.int64)
+    rc = lib().oracle_order(MODES[mode], n, _dp(Dc), seed, mult, int(additive), fallback, _ip(ordering),
+                            _dp(trace) if want_trace else None, max_trace, _lp(ntr), _lp(cnt))
+    if rc != 0:
+        raise RuntimeError(f"oracle_order rc={rc}")
+    return ordering, trace[: int(ntr[0])], {"pair_evals": int(cnt[0]), "npe_would_fire": int(cnt[1]), "D_final": Dc}
+
+
+def rowsums(D):
+    n = D.shape[0]
+    Dc = np.ascontiguousarray(D, dtype=np.float64)
+    out = np.zeros(n, dtype=np.float64)
+    lib().oracle_rowsums(n, _dp(Dc), _dp(out))
+    return out
+
+
+def setup_d(ordering, d_upper):
+    n = len(ordering) - 1
+    o = np.ascontiguousarray(ordering, dtype=np.int32)
+    du = np.ascontiguousarray(d_upper, dtype=np.float64)
+    out = np.zeros(n * (n - 1) // 2, dtype=np.float64)
+    lib().oracle_setup_d(n, _ip(o), _dp(du), _dp(out))
+    return out
+
+
+def _vec(fn, n, v):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.zeros_like(v)
+    fn(n, _dp(v), _dp(out))
+    return out
+
+
+def unconstrained_ls(n, d):
+    return _vec(lib().oracle_unconstrained_ls, n, d)
+
+
+def atx(n, d):
+    return _vec(lib().oracle_atx, n, d)
+
+
+def ab(n, b):
+    return _vec(lib().oracle_ab, n, b)
+
+
+def split_weights(n, d_pos, constrained=True):
+    d = np.ascontiguousarray(d_pos, dtype=np.float64)
+    x = np.zeros_like(d)
+    st = np.zeros(4, dtype=np.int64)
+    lib().oracle_split_weights(n, _dp(d), _dp(x), int(constrained), _lp(st))
+    return x, {"cg_iters": int(st[0]), "cg_calls": int(st[1]), "outer": int(st[2]), "inner": int(st[3])}
+
+
+def java_random(seed, bound, count):
+    out = np.zeros(count, dtype=np.int32)
+    lib().oracle_java_random(seed, bound, count, _ip(out))
+    return out
