@@ -1,0 +1,252 @@
+"""ctypes binding of libfastnn.so plus classes that mirror the reference's operator API.
+
+Reference interface mirrored (argument meaning and error behaviour kept):
+  new NeighborNetCanonical(double[][] D, int nTaxa, int nThreads, ExecutorService pool)
+  new NeighborNetLocal(D, nTaxa, nThreads, boolean additive, pool)
+  new NeighborNetRandom(D, nTaxa, nThreads, pool, RandomAmount amount, int mult)
+  int[] runNeighborNet()                                   (NetMakerOriginal.java:51,129)
+`nThreads`/`pool` are accepted and ignored (single host control thread).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class FastNNError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libfastnn error {code}: {msg}")
+        self.code = code
+
+
+class fnn_opts(ctypes.Structure):
+    _fields_ = [
+        ("mode", ctypes.c_int32),
+        ("mult", ctypes.c_int32),
+        ("additive", ctypes.c_int32),
+        ("canonical_fallback", ctypes.c_int32),
+        ("seed", ctypes.c_int64),
+        ("device", ctypes.c_int32),
+        ("use_graph", ctypes.c_int32),
+        ("record_trace", ctypes.c_int32),
+        ("profile_every", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 6),
+    ]
+
+
+class fnn_stats(ctypes.Structure):
+    _fields_ = [
+        ("iterations", ctypes.c_int64),
+        ("kernel_launches", ctypes.c_int64),
+        ("scan_launches", ctypes.c_int64),
+        ("scan_alg_bytes", ctypes.c_double),
+        ("prof_scan_ms", ctypes.c_double),
+        ("prof_scan_bytes", ctypes.c_double),
+        ("prof_scan_samples", ctypes.c_int64),
+        ("order_ms", ctypes.c_double),
+        ("h2d_ms", ctypes.c_double),
+        ("reserved", ctypes.c_double * 8),
+    ]
+
+
+MODES = {"canonical": 0, "relaxed": 1, "random_n": 2, "random_nlogn": 3, "random_logn": 4}
+
+# every symbol include/fastnn.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "fnn_default_opts", "fnn_last_error", "fnn_device_count", "fnn_ctx_create", "fnn_ctx_destroy",
+    "fnn_ctx_load_host", "fnn_ctx_load_device", "fnn_ctx_synth", "fnn_ctx_read_matrix", "fnn_ctx_order",
+    "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums",
+]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libfastnn.so")
+
+
+def lib():
+    """Load libfastnn.so; fails loudly when the CUDA extension has not been built."""
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise FastNNError(-100, f"{p} is missing: run ./build.sh (nvcc, sm_100a). There is no CPU fallback.")
+        L = ctypes.CDLL(p)
+        vp, c_dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)
+        L.fnn_default_opts.argtypes = [ctypes.POINTER(fnn_opts)]
+        L.fnn_default_opts.restype = None
+        L.fnn_last_error.restype = ctypes.c_char_p
+        L.fnn_device_count.restype = ctypes.c_int
+        L.fnn_ctx_create.argtypes = [ctypes.POINTER(fnn_opts), ctypes.c_int64, ctypes.POINTER(vp)]
+        L.fnn_ctx_destroy.argtypes = [vp]
+        L.fnn_ctx_destroy.restype = None
+        L.fnn_ctx_load_host.argtypes = [vp, c_dp]
+        L.fnn_ctx_load_device.argtypes = [vp, vp, ctypes.c_int64]
+        L.fnn_ctx_synth.argtypes = [vp, c_dp, c_dp, ctypes.POINTER(ctypes.c_int64), ctypes.c_uint64, ctypes.c_double]
+        L.fnn_ctx_read_matrix.argtypes = [vp, c_dp]
+        L.fnn_ctx_order.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
+        L.fnn_ctx_trace.argtypes = [vp, c_dp, ctypes.c_int64]
+        L.fnn_ctx_trace.restype = ctypes.c_int64
+        L.fnn_ctx_stats.argtypes = [vp, ctypes.POINTER(fnn_stats)]
+        L.fnn_ctx_matrix_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
+        L.fnn_order.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
+        L.fnn_rowsums.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int64, c_dp]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise FastNNError(rc, lib().fnn_last_error().decode())
+
+
+def device_count():
+    return lib().fnn_device_count()
+
+
+def default_opts(**kw):
+    o = fnn_opts()
+    lib().fnn_default_opts(ctypes.byref(o))
+    for k, v in kw.items():
+        if k == "mode" and isinstance(v, str):
+            v = MODES[v.lower()]
+        setattr(o, k, int(v))
+    return o
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+class Context:
+    """Device-resident problem of n taxa (fnn_ctx)."""
+
+    def __init__(self, n, **opts):
+        self.n = int(n)
+        self.opts = default_opts(**opts)
+        self._h = ctypes.c_void_p()
+        _check(lib().fnn_ctx_create(ctypes.byref(self.opts), self.n, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().fnn_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_host(self, D):
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        assert D.shape == (self.n, self.n)
+        _check(lib().fnn_ctx_load_host(self._h, _dp(D)))
+
+    def load_device(self, dptr, ld):
+        _check(lib().fnn_ctx_load_device(self._h, ctypes.c_void_p(int(dptr)), int(ld)))
+
+    def synth(self, seed, eps=0.05):
+        from . import synth as _s
+        h, a, pi, inv = _s.tree_params(self.n, seed)
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        inv = np.ascontiguousarray(inv, dtype=np.int64)
+        if h.size == 0:
+            h = np.zeros(1)
+        _check(lib().fnn_ctx_synth(self._h, _dp(h), _dp(a), inv.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                   ctypes.c_uint64(_s.stream_base(seed, 3)), float(eps)))
+
+    def read_matrix(self):
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        _check(lib().fnn_ctx_read_matrix(self._h, _dp(out)))
+        return out
+
+    def matrix_ptr(self):
+        p, ld = ctypes.c_void_p(), ctypes.c_int64()
+        _check(lib().fnn_ctx_matrix_ptr(self._h, ctypes.byref(p), ctypes.byref(ld)))
+        return p.value, ld.value
+
+    def order(self):
+        out = np.zeros(self.n + 1, dtype=np.int32)
+        _check(lib().fnn_ctx_order(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out
+
+    def trace(self):
+        rows = np.zeros((self.n + 8, 8), dtype=np.float64)
+        k = lib().fnn_ctx_trace(self._h, _dp(rows), rows.shape[0])
+        if k < 0:
+            _check(int(k))
+        return rows[: int(k)]
+
+    def stats(self):
+        s = fnn_stats()
+        _check(lib().fnn_ctx_stats(self._h, ctypes.byref(s)))
+        return {f: getattr(s, f) for f, _ in fnn_stats._fields_ if f != "reserved"}
+
+
+def order(D=None, phylip_path=None, n=None, **opts):
+    """One-shot seam B1 (fnn_order): host matrix or Phylip path in, ordering[n+1] out."""
+    o = default_opts(**opts)
+    if D is not None:
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        n = D.shape[0]
+    out = np.zeros(int(n) + 1, dtype=np.int32)
+    _check(lib().fnn_order(ctypes.byref(o), _dp(D) if D is not None else None,
+                           phylip_path.encode() if phylip_path else None, int(n),
+                           out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+    return out
+
+
+def rowsums(D, **opts):
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    o = default_opts(**opts)
+    out = np.zeros(D.shape[0], dtype=np.float64)
+    _check(lib().fnn_rowsums(ctypes.byref(o), _dp(D), D.shape[0], _dp(out)))
+    return out
+
+
+class _NetMaker:
+    """Shape of NetMakerOriginal (NetMakerOriginal.java:51,129): construct with D, call runNeighborNet()."""
+
+    _mode = "canonical"
+
+    def __init__(self, D, numTaxa, numThreads=1, pool=None, **opts):
+        self.D = D
+        self.ntax = int(numTaxa)
+        self.opts = dict(opts)
+        self.opts.setdefault("mode", self._mode)
+        self.ordering = None
+
+    def runNeighborNet(self):
+        self.ordering = order(np.asarray(self.D, dtype=np.float64)[: self.ntax, : self.ntax], **self.opts)
+        return self.ordering
+
+    def getOrdering(self):
+        return self.ordering
+
+
+class NeighborNetCanonical(_NetMaker):
+    """NeighborNetCanonical.java:34."""
+
+
+class NeighborNetLocal(_NetMaker):
+    """NeighborNetLocal.java:26 (relaxed); `additive` as in the reference constructor."""
+
+    def __init__(self, D, numTaxa, numThreads=1, additive=False, pool=None, **opts):
+        super().__init__(D, numTaxa, numThreads, pool, mode="relaxed", additive=int(bool(additive)), **opts)
+
+
+class NeighborNetRandom(_NetMaker):
+    """NeighborNetRandom.java:24; myAmount in {"LOGN","N","NLOGN"}, multiplier as -mult."""
+
+    def __init__(self, D, numTaxa, numThreads=1, pool=None, myAmount="NLOGN", multiplier=5, **opts):
+        super().__init__(D, numTaxa, numThreads, pool, mode="random_" + myAmount.lower(), mult=int(multiplier), **opts)

@@ -1,0 +1,26 @@
+// fnn_common.h — error plumbing shared by the translation units of libfastnn.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include "fastnn.h"
+
+namespace fnn {
+void set_error(const char* fmt, ...);
+const char* last_error();
+}  // namespace fnn
+
+// internal accessors across translation units (not part of the ABI)
+int64_t fnn_ctx_n_(fnn_ctx* c);
+void fnn_ctx_mark_loaded_(fnn_ctx* c);
+
+// CUDA errors are fatal for the call (no CPU fallback): record and return FNN_E_CUDA.
+#define FNN_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t err_ = (call);                                                              \
+        if (err_ != cudaSuccess) {                                                              \
+            fnn::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err_)); \
+            cudaGetLastError();                                                                 \
+            return FNN_E_CUDA;                                                                  \
+        }                                                                                       \
+    } while (0)

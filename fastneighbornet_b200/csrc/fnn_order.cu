@@ -1,0 +1,1052 @@
+// fnn_order.cu — B200-native Neighbor-Net ordering engine (seam B1 of include/fastnn.h).
+//
+// What the reference does (NetMakerOriginal.java:129-162): n-1 agglomeration iterations of
+//   select (Q-criterion argmin over cluster pairs, :197-236 / NeighborNetCanonical.java:150-179)
+//   -> pick node pair among <=4 (ComputeRx, :397-452) -> subtract sweep (:455-461, :681-696)
+//   -> 2/3/4-way reduction with in-place D update (:570-726) -> add sweep (:517-536),
+// then the circular-order expansion (:246-325).
+//
+// How this file does it (B200-first, not a translation):
+//   * The whole agglomeration state lives in HBM and the loop runs device-side: five kernels
+//     per iteration, no host round trip, replayed as a CUDA graph.  The host only expands
+//     the amalgamation log at the end (expandNodes stays on the host).
+//   * Physical layout != reference layout.  The live nodes occupy matrix slots [0,m):
+//     slots [0,P2) hold the paired clusters as aligned (rep, non-rep) slot pairs, slots
+//     [P2,m) hold the singletons.  Every cluster pair's 1/2/4 cross entries are then one or
+//     two aligned 16-byte loads, the selection scan is a dense coalesced stream over the
+//     lower triangle (each cross-cluster entry read exactly once = the algorithmic bytes of
+//     SURVEY §8d), and the matrix never fragments.  Keeping that layout costs
+//     O(1) row/column moves (<=6 slots) per iteration.
+//   * The reference's scan order is carried as data: pos[slot] is the node's index in the
+//     Java netNodes[] array; the fused min-loc reduces on the key (Q, i, j) = (value, higher
+//     position, lower position), which is exactly "first strict minimum in (i, j<i) order".
+//   * Bit-exactness: compiled with --fmad=false; sums that the reference accumulates
+//     sequentially (ComputeRx, u.Sx) are summed sequentially in position order by one lane
+//     reading shared-memory tiles staged by the rest of the block.
+//
+// No CPU fallback: every entry point fails with FNN_E_NODEVICE when there is no GPU.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "fastnn.h"
+#include "fnn_common.h"
+
+namespace {
+
+constexpr int MAXK = 8;         // changed slots per iteration (<= 6 used)
+constexpr int SRC_NEW_U = -1;   // content marker: the new node u / v of this iteration
+constexpr int SRC_NEW_V = -2;
+
+struct DevState {
+    // committed state
+    int m, c, P2, num_nodes;
+    int iter, done, n_amalg, skip;
+    // selection result (k_scan)
+    double selQ;
+    int sel_i, sel_j;
+    unsigned int ticket;
+    int pad0;
+    // event descriptor (k_pick)
+    int kind;                     // 2, 3, 4; 5 = the 4-active/2-cluster special case
+    int m_new, c_new, P2_new;
+    int fX, fY, fZ, fW;           // formula rows: 3-way (X,Y,Z); 4-way (x2,x,y,y2)
+    int sx, sxn, sy, syn;         // chosen x, x.nbr, y, y.nbr (old slots; -1 = none)
+    int su;                       // base slot of the new cluster (new layout)
+    int K;
+    double Duv;                   // the order-dependent u-v entry
+    int chg_slot[MAXK];
+    int chg_src[MAXK];
+    double chg_Sx[MAXK];
+    int final3[4];
+};
+
+struct Partial { double q; unsigned long long key; };
+
+#define TWO_THIRDS (2.0 / 3.0)
+
+__device__ __forceinline__ bool better(double q, unsigned long long k, double bq, unsigned long long bk) {
+    return (q < bq) || (q == bq && k < bk);
+}
+
+// ------------------------------------------------------------------ init kernels
+__global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) { id[t] = t + 1; pos[t] = t; p2s[t] = t; }
+    if (t == 0) {
+        memset(st, 0, sizeof(DevState));
+        st->m = n; st->c = n; st->P2 = 0; st->num_nodes = n;
+    }
+}
+
+// K1: Sx[k] = sum_{j != k} D[k][j], ascending j (NetMakerOriginal.java:164-191).  Thread k walks
+// column k (== row k by symmetry) so that a warp reads 256 contiguous bytes per step.
+__global__ void k_rowsum(const double* __restrict__ D, int64_t ld, int n, double* Sx) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double s = 0.0;
+    const double* col = D + k;
+#pragma unroll 8
+    for (int j = 0; j < n; ++j) {
+        double v = col[(int64_t)j * ld];
+        if (j != k) s += v;
+    }
+    Sx[k] = s;
+}
+
+__global__ void k_zero_diag(double* D, int64_t ld, int n) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) D[(int64_t)k * ld + k] = 0.0;
+}
+
+// ------------------------------------------------------------------ K2: selection scan
+// Dense lower-triangle stream with fused Q evaluation and (Q, i, j) min-loc.
+// Tile = TR physical rows x 512 columns; thread owns a 16-byte column pair.
+constexpr int SCAN_THREADS = 256;
+constexpr int TILE_W = 2 * SCAN_THREADS;
+
+__device__ __forceinline__ double2 ldg2(const double* p) {
+    return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+template <int TR>
+__global__ void __launch_bounds__(SCAN_THREADS, 2)
+k_scan(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ pos,
+       DevState* st, Partial* partials) {
+    if (st->done) return;
+    const int m = st->m, P2 = st->P2;
+    const double cm2 = (double)st->c - 2.0;
+    constexpr int KPB = TILE_W / TR;  // row tiles per 512-row band
+    __shared__ double rSx[TR];
+    __shared__ int rPos[TR];
+    __shared__ Partial wbest[SCAN_THREADS / 32];
+    __shared__ bool amLast;
+
+    double bq = INFINITY;
+    unsigned long long bk = ~0ull;
+
+    const int nRowTiles = (m + TR - 1) / TR;
+    const int gFull = nRowTiles / KPB, rRem = nRowTiles % KPB;
+    const long long total = (long long)KPB * gFull * (gFull + 1) / 2 + (long long)rRem * (gFull + 1);
+
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        // decode t -> (band g, row tile r within band, column tile ct <= g)
+        long long g = (long long)((sqrt(8.0 * (double)t / KPB + 1.0) - 1.0) * 0.5);
+        while ((long long)KPB * g * (g + 1) / 2 > t) --g;
+        while ((long long)KPB * (g + 1) * (g + 2) / 2 <= t) ++g;
+        long long rem = t - (long long)KPB * g * (g + 1) / 2;
+        const int rloc = (int)(rem / (g + 1));
+        const int ct = (int)(rem % (g + 1));
+        const int r0 = ((int)g * KPB + rloc) * TR;
+        const int c0 = ct * TILE_W + 2 * threadIdx.x;
+
+        __syncthreads();
+        if (threadIdx.x < TR && r0 + threadIdx.x < m) {
+            rSx[threadIdx.x] = Sx[r0 + threadIdx.x];
+            rPos[threadIdx.x] = pos[r0 + threadIdx.x];
+        }
+        __syncthreads();
+
+        const int rEnd = min(r0 + TR, m);
+        if (c0 >= m || c0 >= rEnd) continue;
+        const bool colPair = c0 < P2;
+        const bool cv1 = (c0 + 1 < m);
+        const double cS0 = Sx[c0];
+        const int cP0 = pos[c0];
+        const double cS1 = cv1 ? Sx[c0 + 1] : 0.0;
+        const int cP1 = cv1 ? pos[c0 + 1] : 0;
+        const double* base = D + c0;
+
+        if (colPair) {
+            // ---- pair rows x pair column: 2x2 block, role-ordered 4-term mean
+            const int rPairEnd = min(rEnd, P2);
+            int r = r0;
+            constexpr int U = 4;
+            for (; r < rPairEnd; r += 2 * U) {
+                double2 e0[U], e1[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int rr = r + 2 * u;
+                    if (rr < rPairEnd && c0 < rr) {
+                        e0[u] = ldg2(base + (int64_t)rr * ld);
+                        e1[u] = ldg2(base + (int64_t)(rr + 1) * ld);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int rr = r + 2 * u;
+                    if (rr < rPairEnd && c0 < rr) {
+                        const int rp = rPos[rr - r0];
+                        const double rS = rSx[rr - r0];
+                        const bool rowP = rp > cP0;  // the row cluster plays "p" (higher position)
+                        const double t1 = rowP ? e0[u].y : e1[u].x;
+                        const double t2 = rowP ? e1[u].x : e0[u].y;
+                        const double dpq = (((e0[u].x + t1) + t2) + e1[u].y) * 0.25;
+                        const double s1 = rowP ? rS : cS0;
+                        const double s2 = rowP ? cS0 : rS;
+                        const double q = (cm2 * dpq - s1) - s2;
+                        if (q <= bq) {
+                            const unsigned long long key = rowP ? (((unsigned long long)rp << 32) | (unsigned)cP0)
+                                                                : (((unsigned long long)cP0 << 32) | (unsigned)rp);
+                            if (better(q, key, bq, bk)) { bq = q; bk = key; }
+                        }
+                    }
+                }
+            }
+            // ---- single rows x pair column: 2-term mean
+            constexpr int U2 = 8;
+            for (r = max(r0, P2); r < rEnd; r += U2) {
+                double2 e[U2];
+#pragma unroll
+                for (int u = 0; u < U2; ++u)
+                    if (r + u < rEnd) e[u] = ldg2(base + (int64_t)(r + u) * ld);
+#pragma unroll
+                for (int u = 0; u < U2; ++u) {
+                    const int rr = r + u;
+                    if (rr < rEnd) {
+                        const int rp = rPos[rr - r0];
+                        const double rS = rSx[rr - r0];
+                        const bool rowP = rp > cP0;
+                        const double dpq = (e[u].x + e[u].y) * 0.5;
+                        const double s1 = rowP ? rS : cS0;
+                        const double s2 = rowP ? cS0 : rS;
+                        const double q = (cm2 * dpq - s1) - s2;
+                        if (q <= bq) {
+                            const unsigned long long key = rowP ? (((unsigned long long)rp << 32) | (unsigned)cP0)
+                                                                : (((unsigned long long)cP0 << 32) | (unsigned)rp);
+                            if (better(q, key, bq, bk)) { bq = q; bk = key; }
+                        }
+                    }
+                }
+            }
+        } else {
+            // ---- single rows x two single columns
+            constexpr int U2 = 8;
+            for (int r = max(max(r0, P2), c0 + 1); r < rEnd; r += U2) {
+                double2 e[U2];
+#pragma unroll
+                for (int u = 0; u < U2; ++u)
+                    if (r + u < rEnd) e[u] = ldg2(base + (int64_t)(r + u) * ld);
+#pragma unroll
+                for (int u = 0; u < U2; ++u) {
+                    const int rr = r + u;
+                    if (rr < rEnd) {
+                        const int rp = rPos[rr - r0];
+                        const double rS = rSx[rr - r0];
+                        {   // column c0 (c0 < rr holds by loop start)
+                            const bool rowP = rp > cP0;
+                            const double s1 = rowP ? rS : cS0;
+                            const double s2 = rowP ? cS0 : rS;
+                            const double q = (cm2 * e[u].x - s1) - s2;
+                            if (q <= bq) {
+                                const unsigned long long key = rowP ? (((unsigned long long)rp << 32) | (unsigned)cP0)
+                                                                    : (((unsigned long long)cP0 << 32) | (unsigned)rp);
+                                if (better(q, key, bq, bk)) { bq = q; bk = key; }
+                            }
+                        }
+                        if (c0 + 1 < rr) {
+                            const bool rowP = rp > cP1;
+                            const double s1 = rowP ? rS : cS1;
+                            const double s2 = rowP ? cS1 : rS;
+                            const double q = (cm2 * e[u].y - s1) - s2;
+                            if (q <= bq) {
+                                const unsigned long long key = rowP ? (((unsigned long long)rp << 32) | (unsigned)cP1)
+                                                                    : (((unsigned long long)cP1 << 32) | (unsigned)rp);
+                                if (better(q, key, bq, bk)) { bq = q; bk = key; }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- block min-loc, then the last block to finish reduces the per-block partials
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double oq = __shfl_down_sync(0xffffffffu, bq, off);
+        unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, off);
+        if (better(oq, ok, bq, bk)) { bq = oq; bk = ok; }
+    }
+    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = Partial{bq, bk};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < SCAN_THREADS / 32; ++w)
+            if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
+        partials[blockIdx.x] = Partial{bq, bk};
+        __threadfence();
+        unsigned int tk = atomicAdd(&st->ticket, 1u);
+        amLast = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (amLast) {
+        __threadfence();
+        bq = INFINITY; bk = ~0ull;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += SCAN_THREADS) {
+            const double pq = __ldcg(&partials[b].q);
+            const unsigned long long pk = __ldcg(&partials[b].key);
+            if (better(pq, pk, bq, bk)) { bq = pq; bk = pk; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double oq = __shfl_down_sync(0xffffffffu, bq, off);
+            unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, off);
+            if (better(oq, ok, bq, bk)) { bq = oq; bk = ok; }
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = Partial{bq, bk};
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < SCAN_THREADS / 32; ++w)
+                if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
+            st->selQ = bq;
+            st->sel_i = (int)(bk >> 32);
+            st->sel_j = (int)(bk & 0xffffffffu);
+            st->ticket = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ sequential chains
+// Sum NR rows of length len strictly left to right (the reference's accumulation order).
+// All threads stage tiles into shared memory through `load(row, i)`; lane r of warp 0 owns
+// chain r.  Double-buffered so the staging of tile k+1 overlaps the dependent adds of tile k.
+constexpr int CH_TILE = 1024;
+
+template <int NR, typename Loader>
+__device__ void block_seq_sum(double (*buf)[NR][CH_TILE], int len, Loader load, double* out /*[NR]*/) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int ntiles = (len + CH_TILE - 1) / CH_TILE;
+    double acc = 0.0;
+    // prologue: tile 0
+    for (int e = tid; e < NR * CH_TILE; e += nt) {
+        int r = e / CH_TILE, i = e % CH_TILE;
+        buf[0][r][i] = (i < len) ? load(r, i) : 0.0;
+    }
+    __syncthreads();
+    for (int t = 0; t < ntiles; ++t) {
+        const int cur = t & 1;
+        if (tid >= 32) {
+            if (t + 1 < ntiles) {
+                const int b0 = (t + 1) * CH_TILE;
+                for (int e = tid - 32; e < NR * CH_TILE; e += nt - 32) {
+                    int r = e / CH_TILE, i = e % CH_TILE;
+                    buf[cur ^ 1][r][i] = (b0 + i < len) ? load(r, b0 + i) : 0.0;
+                }
+            }
+        } else if (tid < NR) {
+            const int cnt = min(CH_TILE, len - t * CH_TILE);
+            const double* row = buf[cur][tid];
+            int i = 0;
+            for (; i + 8 <= cnt; i += 8) {
+                double v0 = row[i], v1 = row[i + 1], v2 = row[i + 2], v3 = row[i + 3];
+                double v4 = row[i + 4], v5 = row[i + 5], v6 = row[i + 6], v7 = row[i + 7];
+                acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
+            }
+            for (; i < cnt; ++i) acc += row[i];
+        }
+        __syncthreads();
+    }
+    if (tid < NR) out[tid] = acc;
+    __syncthreads();
+}
+
+__device__ __forceinline__ int nbr_of(int s, int P2) { return s < P2 ? (s ^ 1) : -1; }
+
+// reference netNodes[y.pos] = netNodes[num_active-1] (NetMakerOriginal.java:641-643) on the
+// position attributes; posU/posV are the not-yet-placed new nodes.
+__device__ void remove_pos(int* pos, int* p2s, int m_cur, int yp, int& posU, int& posV) {
+    const int last = m_cur - 1;
+    if (yp == last) return;
+    if (posU == last) posU = yp;
+    else if (posV == last) posV = yp;
+    else { int L = p2s[last]; pos[L] = yp; p2s[yp] = L; }
+}
+
+// the order-dependent D[u][v] of agg3way (NetMakerOriginal.java:653-657)
+__device__ __forceinline__ double duv_rule(bool uFirst, double dZX, double dYX, double dYZ) {
+    if (uFirst) { double A = TWO_THIRDS * dZX + dYX / 3.0; return TWO_THIRDS * A + dYZ / 3.0; }
+    double B = TWO_THIRDS * dZX + dYZ / 3.0;
+    return TWO_THIRDS * B + dYX / 3.0;
+}
+
+// ------------------------------------------------------------------ K3: pick + bookkeeping (one block)
+constexpr int PICK_THREADS = 1024;
+
+__global__ void __launch_bounds__(PICK_THREADS, 1)
+k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState* st, int* amalg, double* trace) {
+    extern __shared__ unsigned char smem_raw[];
+    double (*buf)[4][CH_TILE] = reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw);
+    __shared__ int sh[8];
+    __shared__ double rx[4];
+    if (st->done) return;
+    const int m = st->m, c = st->c, P2 = st->P2;
+    const int tid = threadIdx.x;
+
+    // ---- special case: 4 active nodes in 2 clusters (NetMakerOriginal.java:343-360)
+    if (m == 4 && c == 2) {
+        if (tid == 0) {
+            const int p = p2s[0], pn = p ^ 1;
+            const int q = (p2s[1] != pn) ? p2s[1] : p2s[2];
+            const int qn = q ^ 1;
+            auto d = [&](int a, int b) { return D[(int64_t)a * ld + b]; };
+            int X = p, Y, Z;
+            if (d(p, q) + d(pn, qn) < d(p, qn) + d(pn, q)) { Y = q; Z = qn; } else { Y = qn; Z = q; }
+            const int nn = st->num_nodes;
+            int posU = pos[X], posV = pos[Z];
+            remove_pos(pos, p2s, 4, pos[Y], posU, posV);
+            int* lg = amalg + 5 * st->n_amalg;
+            lg[0] = nn + 1; lg[1] = nn + 2; lg[2] = id[X]; lg[3] = id[Y]; lg[4] = id[Z];
+            st->n_amalg += 1;
+            st->num_nodes = nn + 2;
+            st->final3[pos[pn]] = id[pn];
+            st->final3[posU] = nn + 1;
+            st->final3[posV] = nn + 2;
+            if (trace) {
+                double* tr = trace + 8 * (int64_t)st->iter;
+                tr[0] = 4; tr[1] = 2; tr[2] = id[p]; tr[3] = id[q]; tr[4] = id[Y]; tr[5] = 0; tr[6] = 5; tr[7] = 0.0;
+            }
+            st->iter += 1;
+            st->done = 1;
+            st->skip = 1;
+        }
+        return;
+    }
+
+    // ---- Cx, Cy from the scan key; id-order swap (:376-380)
+    if (tid == 0) {
+        int cx = p2s[st->sel_i], cy = p2s[st->sel_j];
+        if (id[cx] > id[cy]) { int t = cx; cx = cy; cy = t; }
+        sh[0] = cx; sh[1] = nbr_of(cx, P2); sh[2] = cy; sh[3] = nbr_of(cy, P2);
+    }
+    __syncthreads();
+    const int Cx = sh[0], Cxn = sh[1], Cy = sh[2], Cyn = sh[3];
+
+    // ---- ComputeRx x<=4 (:413-420, :549-561): sequential in position order
+    if (Cxn >= 0 || Cyn >= 0) {
+        const int zs[4] = {Cx, Cxn, Cy, Cyn};
+        auto load = [&](int r, int i) -> double {
+            const int z = zs[r];
+            if (z < 0) return 0.0;
+            const int s = p2s[i];
+            const double v = D[(int64_t)z * ld + s];
+            const bool full = (s >= P2) || s == Cx || s == Cxn || s == Cy || s == Cyn;
+            return full ? v : v * 0.5;
+        };
+        block_seq_sum<4>(buf, m, load, rx);
+    } else {
+        if (tid < 4) rx[tid] = 0.0;
+        __syncthreads();
+    }
+
+    if (tid != 0) return;
+    // ================= single-thread control: everything below is O(1) =================
+    auto d = [&](int a, int b) { return D[(int64_t)a * ld + b]; };
+    int x = Cx, y = Cy;
+    {
+        int mm = c + (Cxn >= 0) + (Cyn >= 0);
+        const double f = (double)mm - 2.0;
+        double best = (f * d(Cx, Cy) - rx[0]) - rx[2];
+        if (Cxn >= 0) { double q = (f * d(Cxn, Cy) - rx[1]) - rx[2]; if (q < best) { x = Cxn; y = Cy; best = q; } }
+        if (Cyn >= 0) { double q = (f * d(Cx, Cyn) - rx[0]) - rx[3]; if (q < best) { x = Cx; y = Cyn; best = q; } }
+        if (Cxn >= 0 && Cyn >= 0) { double q = (f * d(Cxn, Cyn) - rx[1]) - rx[3]; if (q < best) { x = Cxn; y = Cyn; best = q; } }
+        if (trace) {
+            double* tr = trace + 8 * (int64_t)st->iter;
+            tr[0] = m; tr[1] = c; tr[2] = id[Cx]; tr[3] = id[Cy]; tr[4] = id[x]; tr[5] = id[y]; tr[7] = best;
+        }
+    }
+    const int xn = nbr_of(x, P2), yn = nbr_of(y, P2);
+    st->sx = x; st->sxn = xn; st->sy = y; st->syn = yn;
+    const int nn = st->num_nodes;
+    int K = 0;
+    int cslot[MAXK], csrc[MAXK], cid[MAXK], cpos[MAXK];
+    auto add_old = [&](int slot, int src) { cslot[K] = slot; csrc[K] = src; cid[K] = id[src]; cpos[K] = pos[src]; ++K; };
+    auto add_new = [&](int slot, int marker, int nid, int npos) { cslot[K] = slot; csrc[K] = marker; cid[K] = nid; cpos[K] = npos; ++K; };
+    int kind;
+    if (xn < 0 && yn < 0) {
+        // ---------- 2-way (:462-464, :570-577): x (smaller id) becomes the representative
+        kind = 2;
+        const int T0 = P2, T1 = P2 + 1;
+        add_old(T0, x);
+        add_old(T1, y);
+        int vac[2], nv = 0, dsp[2], ndp = 0;
+        if (x != T0 && x != T1) vac[nv++] = x;
+        if (y != T0 && y != T1) vac[nv++] = y;
+        if (T0 != x && T0 != y) dsp[ndp++] = T0;
+        if (T1 != x && T1 != y) dsp[ndp++] = T1;
+        for (int i = 0; i < nv; ++i) add_old(vac[i], dsp[i]);
+        st->m_new = m; st->c_new = c - 1; st->P2_new = P2 + 2; st->su = T0;
+        st->fX = st->fY = st->fZ = st->fW = -1;
+        st->Duv = 0.0;
+    } else if (xn < 0 || yn < 0) {
+        // ---------- 3-way (:465-482, :589-674): X isolated, (Y,Z) a pair
+        kind = 3;
+        const int X = (xn < 0) ? x : y;
+        const int Y = (xn < 0) ? y : x;
+        const int Z = Y ^ 1;
+        int posU = pos[X], posV = pos[Z];
+        const int idX = id[X], idY = id[Y], idZ = id[Z];
+        remove_pos(pos, p2s, m, pos[Y], posU, posV);
+        st->Duv = duv_rule(posU < posV, d(Z, X), d(Y, X), d(Y, Z));
+        const int b = Y & ~1;
+        add_new(b, SRC_NEW_U, nn + 1, posU);
+        add_new(b + 1, SRC_NEW_V, nn + 2, posV);
+        if (X != m - 1) add_old(X, m - 1);
+        int* lg = amalg + 5 * st->n_amalg;
+        lg[0] = nn + 1; lg[1] = nn + 2; lg[2] = idX; lg[3] = idY; lg[4] = idZ;
+        st->n_amalg += 1;
+        st->num_nodes = nn + 2;
+        st->m_new = m - 1; st->c_new = c - 1; st->P2_new = P2; st->su = b;
+        st->fX = X; st->fY = Y; st->fZ = Z; st->fW = -1;
+    } else {
+        // ---------- 4-way (:483-487, :707-726): agg3way(x2,x,y) then agg3way(u,u.nbr,y2)
+        kind = 4;
+        const int x2 = xn, y2 = yn;
+        int posU = pos[x2], posV = pos[y];
+        const int idx2 = id[x2], idx = id[x], idy = id[y], idy2 = id[y2];
+        remove_pos(pos, p2s, m, pos[x], posU, posV);
+        const double duv1 = duv_rule(posU < posV, d(y, x2), d(x, x2), d(x, y));
+        const double u1y2 = TWO_THIRDS * d(x2, y2) + d(x, y2) / 3.0;
+        const double v1y2 = TWO_THIRDS * d(y, y2) + d(x, y2) / 3.0;
+        int posU2 = posU, posV2 = pos[y2];
+        remove_pos(pos, p2s, m - 1, posV, posU2, posV2);
+        st->Duv = duv_rule(posU2 < posV2, u1y2, duv1, v1y2);
+        int* lg = amalg + 5 * st->n_amalg;
+        lg[0] = nn + 1; lg[1] = nn + 2; lg[2] = idx2; lg[3] = idx; lg[4] = idy;
+        lg[5] = nn + 3; lg[6] = nn + 4; lg[7] = nn + 1; lg[8] = nn + 2; lg[9] = idy2;
+        st->n_amalg += 2;
+        st->num_nodes = nn + 4;
+        const int bx = x & ~1, by = y & ~1;
+        const int A = min(bx, by), B = max(bx, by), Lp = P2 - 2;
+        add_new(A, SRC_NEW_U, nn + 3, posU2);
+        add_new(A + 1, SRC_NEW_V, nn + 4, posV2);
+        if (B != Lp) { add_old(B, Lp); add_old(B + 1, Lp + 1); }
+        const int S = m - P2;
+        if (S >= 2) { add_old(Lp, m - 2); add_old(Lp + 1, m - 1); }
+        else if (S == 1) { add_old(Lp, m - 1); }
+        st->m_new = m - 2; st->c_new = c - 1; st->P2_new = P2 - 2; st->su = A;
+        st->fX = x2; st->fY = x; st->fZ = y; st->fW = y2;
+    }
+    if (trace) trace[8 * (int64_t)st->iter + 6] = kind;
+    st->kind = kind;
+    st->K = K;
+    // publish the new layout's node tables (sources were captured above, so overlaps are safe)
+    for (int k = 0; k < K; ++k) {
+        st->chg_slot[k] = cslot[k];
+        st->chg_src[k] = csrc[k];
+        st->chg_Sx[k] = 0.0;
+    }
+    for (int k = 0; k < K; ++k) {
+        id[cslot[k]] = cid[k];
+        pos[cslot[k]] = cpos[k];
+        p2s[cpos[k]] = cslot[k];
+    }
+    st->skip = 0;
+}
+
+// formula rows of the new nodes at old column a (bystander columns; order independent)
+struct Formula {
+    int kind, X, Y, Z, W;
+    __device__ __forceinline__ void eval(const double* D, int64_t ld, int a, double& fu, double& fv) const {
+        if (kind == 3) {
+            const double dx = D[(int64_t)X * ld + a], dy = D[(int64_t)Y * ld + a], dz = D[(int64_t)Z * ld + a];
+            fu = TWO_THIRDS * dx + dy / 3.0;
+            fv = TWO_THIRDS * dz + dy / 3.0;
+        } else {  // 4-way: (x2, x, y, y2) = (X, Y, Z, W)
+            const double dx2 = D[(int64_t)X * ld + a], dx = D[(int64_t)Y * ld + a];
+            const double dy = D[(int64_t)Z * ld + a], dy2 = D[(int64_t)W * ld + a];
+            const double u1 = TWO_THIRDS * dx2 + dx / 3.0;
+            const double v1 = TWO_THIRDS * dy + dx / 3.0;
+            fu = TWO_THIRDS * u1 + v1 / 3.0;
+            fv = TWO_THIRDS * dy2 + v1 / 3.0;
+        }
+    }
+};
+
+// cluster distance D(p-cluster, x) in the subtract sweep's role order (:681-696): p the
+// bystander representative (even slot if paired), x the chosen node, xn its neighbour or -1.
+__device__ __forceinline__ double sub_dist(const double* D, int64_t ld, int p, bool pPair, int x, int xn) {
+    const double* rx = D + (int64_t)x * ld;
+    if (xn < 0) {
+        if (!pPair) return rx[p];
+        return (rx[p] + rx[p + 1]) * 0.5;
+    }
+    const double* rxn = D + (int64_t)xn * ld;
+    if (!pPair) return (rx[p] + rxn[p]) * 0.5;
+    return (((rx[p] + rxn[p]) + rx[p + 1]) + rxn[p + 1]) * 0.25;
+}
+
+// ------------------------------------------------------------------ K4+K5a: subtract sweep + build changed rows
+__global__ void __launch_bounds__(256)
+k_rows(const double* __restrict__ D, int64_t ld, double* Sx, DevState* st, double* scratch) {
+    if (st->done || st->skip) return;
+    const int m = st->m, P2 = st->P2, m_new = st->m_new, K = st->K;
+    __shared__ int cslot[MAXK], csrc[MAXK];
+    if (threadIdx.x < MAXK) { cslot[threadIdx.x] = st->chg_slot[threadIdx.x]; csrc[threadIdx.x] = st->chg_src[threadIdx.x]; }
+    __syncthreads();
+    const int x = st->sx, xn = st->sxn, y = st->sy, yn = st->syn;
+    const int xb = (xn >= 0) ? (x & ~1) : x, yb = (yn >= 0) ? (y & ~1) : y;
+    Formula F{st->kind, st->fX, st->fY, st->fZ, st->fW};
+    const double Duv = st->Duv;
+
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
+        // ---- role 1: subtract old cluster distances (old layout), bystander representatives only
+        {
+            const int s = t;
+            const bool pPair = s < P2;
+            if (!(pPair && (s & 1)) && s != xb && s != yb) {
+                const double dpx = sub_dist(D, ld, s, pPair, x, xn);
+                const double dpy = sub_dist(D, ld, s, pPair, y, yn);
+                const double ns = (Sx[s] - dpx) - dpy;
+                Sx[s] = ns;
+                double nb = 0.0;
+                if (pPair) { nb = (Sx[s + 1] - dpx) - dpy; Sx[s + 1] = nb; }
+                for (int k = 0; k < K; ++k) {
+                    if (csrc[k] == s) st->chg_Sx[k] = ns;
+                    if (pPair && csrc[k] == s + 1) st->chg_Sx[k] = nb;
+                }
+            }
+        }
+        // ---- role 2: rows of the changed slots in the NEW layout, column t
+        if (t < m_new) {
+            int colsrc = t;
+            for (int k = 0; k < K; ++k) if (cslot[k] == t) colsrc = csrc[k];
+            double fu = 0.0, fv = 0.0;
+            bool haveF = false;
+            for (int k = 0; k < K; ++k) {
+                const int rs = csrc[k];
+                double v;
+                if (rs >= 0) {
+                    if (colsrc >= 0) v = D[(int64_t)rs * ld + colsrc];
+                    else { double a, b; F.eval(D, ld, rs, a, b); v = (colsrc == SRC_NEW_U) ? a : b; }
+                } else {
+                    if (colsrc >= 0) {
+                        if (!haveF) { F.eval(D, ld, colsrc, fu, fv); haveF = true; }
+                        v = (rs == SRC_NEW_U) ? fu : fv;
+                    } else v = (rs == colsrc) ? 0.0 : Duv;
+                }
+                scratch[(int64_t)k * ld + t] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K5b+K6a: scatter rows/cols + add sweep
+__global__ void __launch_bounds__(256)
+k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevState* st, const double* __restrict__ scratch,
+          double* stage) {
+    if (st->done || st->skip) return;
+    const int m_new = st->m_new, P2n = st->P2_new, K = st->K, su = st->su;
+    __shared__ int cslot[MAXK];
+    __shared__ double cSx[MAXK];
+    if (threadIdx.x < MAXK) { cslot[threadIdx.x] = st->chg_slot[threadIdx.x]; cSx[threadIdx.x] = st->chg_Sx[threadIdx.x]; }
+    __syncthreads();
+    const double* r0 = scratch;        // row of u  (chg index 0 is always su)
+    const double* r1 = scratch + ld;   // row of u' (chg index 1 is always su+1)
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m_new; t += gridDim.x * blockDim.x) {
+        for (int k = 0; k < K; ++k) {
+            const double v = scratch[(int64_t)k * ld + t];
+            const int s = cslot[k];
+            D[(int64_t)s * ld + t] = v;
+            D[(int64_t)t * ld + s] = v;
+        }
+        // add new cluster distances (updateClusterDistances, :517-536)
+        const bool pPair = t < P2n;
+        if (pPair && (t & 1)) continue;
+        if (t == su) {
+            stage[pos[t]] = 0.0;
+            stage[pos[t + 1]] = 0.0;
+            continue;
+        }
+        double base0 = Sx[t], base1 = pPair ? Sx[t + 1] : 0.0;
+        for (int k = 0; k < K; ++k) {
+            if (cslot[k] == t) base0 = cSx[k];
+            if (pPair && cslot[k] == t + 1) base1 = cSx[k];
+        }
+        double dpu;
+        if (pPair) dpu = (((r0[t] + r1[t]) + r0[t + 1]) + r1[t + 1]) * 0.25;
+        else dpu = (r0[t] + r1[t]) * 0.5;
+        Sx[t] = base0 + dpu;
+        stage[pos[t]] = dpu;
+        if (pPair) { Sx[t + 1] = base1 + dpu; stage[pos[t + 1]] = 0.0; }
+    }
+}
+
+// ------------------------------------------------------------------ K6b: u.Sx chain + commit
+__global__ void __launch_bounds__(PICK_THREADS, 1)
+k_chain(double* Sx, const int* id, const int* p2s, DevState* st, const double* __restrict__ stage) {
+    extern __shared__ unsigned char smem_raw[];
+    double (*buf)[1][CH_TILE] = reinterpret_cast<double (*)[1][CH_TILE]>(smem_raw);
+    __shared__ double tot[1];
+    if (st->done || st->skip) return;
+    const int m_new = st->m_new;
+    auto load = [&](int, int i) -> double { return stage[i]; };
+    block_seq_sum<1>(buf, m_new, load, tot);
+    if (threadIdx.x == 0) {
+        const int su = st->su;
+        Sx[su] = tot[0];
+        Sx[su + 1] = tot[0];
+        st->m = m_new; st->c = st->c_new; st->P2 = st->P2_new;
+        st->iter += 1;
+        if (m_new <= 3) {
+            st->done = 1;
+            for (int i = 0; i < 3; ++i) st->final3[i] = id[p2s[i]];
+        }
+    }
+}
+
+}  // namespace
+
+// ============================================================================ host side
+struct fnn_ctx {
+    fnn_opts o;
+    int64_t n = 0, ld = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    double* D = nullptr;
+    double* Sx = nullptr;
+    double* scratch = nullptr;
+    double* stage = nullptr;
+    double* trace = nullptr;
+    int *id = nullptr, *pos = nullptr, *p2s = nullptr, *amalg = nullptr;
+    DevState* st = nullptr;
+    Partial* partials = nullptr;
+    int scan_grid = 0, row_grid = 0;
+    DevState* h_st = nullptr;  // pinned
+    cudaGraphExec_t graph = nullptr;
+    int graph_iters = 0;
+    bool loaded = false;
+    fnn_stats stats{};
+    int64_t trace_rows = 0;
+};
+
+static int ensure_device(const fnn_opts* o) {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt <= 0) {
+        fnn::set_error("no CUDA device available (libfastnn has no CPU fallback): %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return FNN_E_NODEVICE;
+    }
+    int dev = o ? o->device : 0;
+    if (dev < 0 || dev >= cnt) { fnn::set_error("device %d out of range (%d devices)", dev, cnt); return FNN_E_ARG; }
+    FNN_CUDA(cudaSetDevice(dev));
+    return FNN_OK;
+}
+
+extern "C" void fnn_default_opts(fnn_opts* o) {
+    memset(o, 0, sizeof(*o));
+    o->mode = FNN_CANONICAL;
+    o->mult = 5;
+    o->canonical_fallback = 1024;
+    o->seed = 12345;
+    o->use_graph = 1;
+}
+
+extern "C" const char* fnn_last_error(void) { return fnn::last_error(); }
+
+extern "C" int fnn_device_count(void) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return cnt;
+}
+
+extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->o.device);
+    if (c->graph) cudaGraphExecDestroy(c->graph);
+    cudaFree(c->D); cudaFree(c->Sx); cudaFree(c->scratch); cudaFree(c->stage); cudaFree(c->trace);
+    cudaFree(c->id); cudaFree(c->pos); cudaFree(c->p2s); cudaFree(c->amalg); cudaFree(c->st); cudaFree(c->partials);
+    if (c->h_st) cudaFreeHost(c->h_st);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
+    if (!out || n < 1) { fnn::set_error("fnn_ctx_create: bad arguments"); return FNN_E_ARG; }
+    fnn_opts d;
+    if (!o) { fnn_default_opts(&d); o = &d; }
+    if (n > 2000000) { fnn::set_error("n too large"); return FNN_E_ARG; }
+    if (o->mode != FNN_CANONICAL && n > o->canonical_fallback) {
+        fnn::set_error("mode %d is not implemented on the device yet (canonical only)", o->mode);
+        return FNN_E_UNSUPPORTED;
+    }
+    int rc = ensure_device(o);
+    if (rc) return rc;
+    fnn_ctx* c = new fnn_ctx();
+    c->o = *o;
+    c->n = n;
+    c->ld = (n + 15) / 16 * 16;
+    cudaDeviceProp prop;
+    FNN_CUDA(cudaGetDeviceProperties(&prop, o->device));
+    c->sms = prop.multiProcessorCount;
+#define FNN_ALLOC(ptr, bytes)                                                                  \
+    do {                                                                                       \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                  \
+        if (e_ != cudaSuccess) {                                                               \
+            fnn::set_error("cudaMalloc(%zu bytes) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); \
+            cudaGetLastError();                                                                \
+            fnn_ctx_destroy(c);                                                                \
+            return FNN_E_NOMEM;                                                                \
+        }                                                                                      \
+    } while (0)
+    FNN_ALLOC(c->D, sizeof(double) * n * c->ld);
+    FNN_ALLOC(c->Sx, sizeof(double) * c->ld);
+    FNN_ALLOC(c->scratch, sizeof(double) * MAXK * c->ld);
+    FNN_ALLOC(c->stage, sizeof(double) * c->ld);
+    FNN_ALLOC(c->id, sizeof(int) * c->ld);
+    FNN_ALLOC(c->pos, sizeof(int) * c->ld);
+    FNN_ALLOC(c->p2s, sizeof(int) * c->ld);
+    FNN_ALLOC(c->amalg, sizeof(int) * 5 * (2 * n + 8));
+    FNN_ALLOC(c->st, sizeof(DevState));
+    c->scan_grid = c->sms * 2;
+    c->row_grid = std::max<int>(1, std::min<int64_t>((n + 255) / 256, c->sms * 4));
+    FNN_ALLOC(c->partials, sizeof(Partial) * c->scan_grid);
+    if (o->record_trace) FNN_ALLOC(c->trace, sizeof(double) * 8 * (n + 8));
+    FNN_CUDA(cudaMallocHost((void**)&c->h_st, sizeof(DevState)));
+    FNN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    FNN_CUDA(cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 4 * CH_TILE * sizeof(double))));
+    FNN_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 1 * CH_TILE * sizeof(double))));
+    *out = c;
+    return FNN_OK;
+}
+
+static int after_load(fnn_ctx* c) {
+    const int n = (int)c->n;
+    k_zero_diag<<<(n + 255) / 256, 256, 0, c->stream>>>(c->D, c->ld, n);
+    FNN_CUDA(cudaGetLastError());
+    c->loaded = true;
+    return FNN_OK;
+}
+
+extern "C" int fnn_ctx_load_host(fnn_ctx* c, const double* Dh) {
+    if (!c || !Dh) { fnn::set_error("fnn_ctx_load_host: null argument"); return FNN_E_ARG; }
+    FNN_CUDA(cudaSetDevice(c->o.device));
+    cudaEvent_t e0, e1;
+    FNN_CUDA(cudaEventCreate(&e0)); FNN_CUDA(cudaEventCreate(&e1));
+    FNN_CUDA(cudaEventRecord(e0, c->stream));
+    FNN_CUDA(cudaMemcpy2DAsync(c->D, c->ld * sizeof(double), Dh, c->n * sizeof(double), c->n * sizeof(double), c->n,
+                               cudaMemcpyHostToDevice, c->stream));
+    FNN_CUDA(cudaEventRecord(e1, c->stream));
+    int rc = after_load(c);
+    FNN_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->stats.h2d_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+extern "C" int fnn_ctx_load_device(fnn_ctx* c, const double* dD, int64_t ld_src) {
+    if (!c || !dD || ld_src < c->n) { fnn::set_error("fnn_ctx_load_device: bad argument"); return FNN_E_ARG; }
+    FNN_CUDA(cudaSetDevice(c->o.device));
+    FNN_CUDA(cudaMemcpy2DAsync(c->D, c->ld * sizeof(double), dD, ld_src * sizeof(double), c->n * sizeof(double), c->n,
+                               cudaMemcpyDeviceToDevice, c->stream));
+    int rc = after_load(c);
+    FNN_CUDA(cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
+extern "C" int fnn_ctx_read_matrix(fnn_ctx* c, double* out) {
+    if (!c || !out || !c->loaded) { fnn::set_error("fnn_ctx_read_matrix: no matrix loaded"); return FNN_E_STATE; }
+    FNN_CUDA(cudaSetDevice(c->o.device));
+    FNN_CUDA(cudaMemcpy2DAsync(out, c->n * sizeof(double), c->D, c->ld * sizeof(double), c->n * sizeof(double), c->n,
+                               cudaMemcpyDeviceToHost, c->stream));
+    FNN_CUDA(cudaStreamSynchronize(c->stream));
+    return FNN_OK;
+}
+
+extern "C" int fnn_ctx_matrix_ptr(fnn_ctx* c, double** dptr, int64_t* ld) {
+    if (!c || !dptr || !ld) { fnn::set_error("fnn_ctx_matrix_ptr: null argument"); return FNN_E_ARG; }
+    *dptr = c->D; *ld = c->ld;
+    return FNN_OK;
+}
+
+static inline void launch_scan(fnn_ctx* c) {
+    k_scan<32><<<c->scan_grid, SCAN_THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->partials);
+}
+static inline void launch_rest(fnn_ctx* c) {
+    k_pick<<<1, PICK_THREADS, 2 * 4 * CH_TILE * sizeof(double), c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st,
+                                                                            c->amalg, c->trace);
+    k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
+    k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage);
+    k_chain<<<1, PICK_THREADS, 2 * 1 * CH_TILE * sizeof(double), c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage);
+}
+
+// expandNodes (NetMakerOriginal.java:246-325) on the host from the amalgamation log
+static void expand_order(int64_t n, const std::vector<int>& lg, int n_amalg, const int* final3, int32_t* ordering) {
+    const int maxid = (int)n + 2 * n_amalg + 2;
+    std::vector<int> ch1(maxid + 1, 0), ch2(maxid + 1, 0), nbr(maxid + 1, 0), nxt(maxid + 1, 0), prv(maxid + 1, 0);
+    for (int k = 0; k < n_amalg; ++k) {
+        const int* e = &lg[5 * k];
+        ch1[e[0]] = e[2]; ch2[e[0]] = e[3];
+        ch1[e[1]] = e[3]; ch2[e[1]] = e[4];
+        nbr[e[0]] = e[1]; nbr[e[1]] = e[0];
+    }
+    int x = final3[0], y = final3[1], z = final3[2];
+    nxt[x] = y; nxt[y] = z; nxt[z] = x;
+    prv[x] = z; prv[y] = x; prv[z] = y;
+    for (int k = n_amalg - 1; k >= 0; --k) {
+        int u = lg[5 * k], v = nbr[u];
+        x = ch1[u]; y = ch2[u]; z = ch2[v];
+        if (v != nxt[u]) { std::swap(u, v); std::swap(x, z); }
+        prv[x] = prv[u]; nxt[prv[x]] = x;
+        nxt[x] = y; prv[y] = x;
+        nxt[y] = z; prv[z] = y;
+        nxt[z] = nxt[v]; prv[nxt[z]] = z;
+    }
+    while (x != 1) x = nxt[x];
+    int a = x, t = 0;
+    ordering[0] = 0;
+    do { ordering[++t] = a; a = nxt[a]; } while (a != x && t <= n);
+}
+
+extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
+    if (!c || !ordering) { fnn::set_error("fnn_ctx_order: null argument"); return FNN_E_ARG; }
+    const int64_t n = c->n;
+    if (n <= 3) {  // NetMakerOriginal.java:133-140
+        for (int64_t i = 0; i <= n; ++i) ordering[i] = (int32_t)i;
+        return FNN_OK;
+    }
+    if (!c->loaded) { fnn::set_error("fnn_ctx_order: no matrix loaded"); return FNN_E_STATE; }
+    FNN_CUDA(cudaSetDevice(c->o.device));
+    c->loaded = false;  // the matrix is consumed
+    cudaEvent_t e0, e1;
+    FNN_CUDA(cudaEventCreate(&e0)); FNN_CUDA(cudaEventCreate(&e1));
+    FNN_CUDA(cudaEventRecord(e0, c->stream));
+    const int ni = (int)n;
+    k_init_nodes<<<(ni + 255) / 256, 256, 0, c->stream>>>(ni, c->id, c->pos, c->p2s, c->st);
+    k_rowsum<<<(ni + 127) / 128, 128, 0, c->stream>>>(c->D, c->ld, ni, c->Sx);
+    FNN_CUDA(cudaGetLastError());
+    int64_t launches = 2, scans = 0;
+    const int64_t max_iters = n;  // n-3 .. n-1 iterations; kernels no-op once done
+    double prof_ms = 0.0, prof_bytes = 0.0;
+    int64_t prof_samples = 0;
+
+    if (c->o.profile_every > 0) {
+        // sampled per-launch timing of the selection kernel (roofline.achieved in bench.py)
+        cudaEvent_t p0, p1;
+        FNN_CUDA(cudaEventCreate(&p0)); FNN_CUDA(cudaEventCreate(&p1));
+        for (int64_t it = 0; it < max_iters; ++it) {
+            const bool sample = (it % c->o.profile_every) == 0;
+            if (sample) {
+                FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+                FNN_CUDA(cudaStreamSynchronize(c->stream));
+                if (c->h_st->done) break;
+                FNN_CUDA(cudaEventRecord(p0, c->stream));
+            }
+            launch_scan(c);
+            if (sample) {
+                FNN_CUDA(cudaEventRecord(p1, c->stream));
+                FNN_CUDA(cudaEventSynchronize(p1));
+                float ms = 0;
+                cudaEventElapsedTime(&ms, p0, p1);
+                const double mm = c->h_st->m, pp = c->h_st->P2 / 2;
+                prof_ms += ms;
+                prof_bytes += 4.0 * mm * (mm - 1.0) - 8.0 * pp + 8.0 * mm;
+                ++prof_samples;
+            }
+            launch_rest(c);
+            launches += 5; ++scans;
+        }
+        cudaEventDestroy(p0); cudaEventDestroy(p1);
+        FNN_CUDA(cudaGetLastError());
+    } else if (c->o.use_graph) {
+        constexpr int GI = 16;  // iterations per graph
+        if (!c->graph) {
+            cudaGraph_t g;
+            FNN_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            for (int i = 0; i < GI; ++i) { launch_scan(c); launch_rest(c); }
+            FNN_CUDA(cudaStreamEndCapture(c->stream, &g));
+            FNN_CUDA(cudaGraphInstantiate(&c->graph, g, 0));
+            cudaGraphDestroy(g);
+            c->graph_iters = GI;
+        }
+        int64_t it = 0;
+        while (it < max_iters) {
+            const int64_t batch = 64;  // graphs between done-flag polls
+            for (int64_t b = 0; b < batch && it < max_iters; ++b, it += GI) {
+                FNN_CUDA(cudaGraphLaunch(c->graph, c->stream));
+                launches += 5 * GI; scans += GI;
+            }
+            FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+            FNN_CUDA(cudaStreamSynchronize(c->stream));
+            if (c->h_st->done) break;
+        }
+    } else {
+        int64_t it = 0;
+        while (it < max_iters) {
+            for (int b = 0; b < 256 && it < max_iters; ++b, ++it) {
+                launch_scan(c); launch_rest(c);
+                launches += 5; ++scans;
+            }
+            FNN_CUDA(cudaGetLastError());
+            FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+            FNN_CUDA(cudaStreamSynchronize(c->stream));
+            if (c->h_st->done) break;
+        }
+    }
+    FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+    FNN_CUDA(cudaEventRecord(e1, c->stream));
+    FNN_CUDA(cudaStreamSynchronize(c->stream));
+    FNN_CUDA(cudaGetLastError());
+    if (!c->h_st->done) { fnn::set_error("agglomeration did not terminate (m=%d after %d iterations)", c->h_st->m, c->h_st->iter); return FNN_E_STATE; }
+    const int n_amalg = c->h_st->n_amalg;
+    std::vector<int> lg(5 * (size_t)std::max(n_amalg, 1));
+    FNN_CUDA(cudaMemcpy(lg.data(), c->amalg, sizeof(int) * 5 * n_amalg, cudaMemcpyDeviceToHost));
+    expand_order(n, lg, n_amalg, c->h_st->final3, ordering);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->stats.order_ms = ms;
+    c->stats.iterations = c->h_st->iter;
+    c->stats.kernel_launches = launches;
+    c->stats.scan_launches = scans;
+    c->stats.prof_scan_ms = prof_ms;
+    c->stats.prof_scan_bytes = prof_bytes;
+    c->stats.prof_scan_samples = prof_samples;
+    c->trace_rows = c->h_st->iter;
+    return FNN_OK;
+}
+
+extern "C" int64_t fnn_ctx_trace(fnn_ctx* c, double* rows, int64_t max_rows) {
+    if (!c || !rows || !c->trace) { fnn::set_error("fnn_ctx_trace: trace not recorded (opts.record_trace)"); return FNN_E_STATE; }
+    int64_t k = std::min<int64_t>(c->trace_rows, max_rows);
+    if (cudaMemcpy(rows, c->trace, sizeof(double) * 8 * k, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fnn::set_error("trace copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return FNN_E_CUDA;
+    }
+    return k;
+}
+
+extern "C" int fnn_ctx_stats(fnn_ctx* c, fnn_stats* out) {
+    if (!c || !out) { fnn::set_error("fnn_ctx_stats: null argument"); return FNN_E_ARG; }
+    *out = c->stats;
+    return FNN_OK;
+}
+
+extern "C" int fnn_rowsums(const fnn_opts* o, const double* Dh, int64_t n, double* Sx_out) {
+    fnn_ctx* c = nullptr;
+    int rc = fnn_ctx_create(o, n, &c);
+    if (rc) return rc;
+    rc = fnn_ctx_load_host(c, Dh);
+    if (!rc) {
+        k_rowsum<<<((int)n + 127) / 128, 128, 0, c->stream>>>(c->D, c->ld, (int)n, c->Sx);
+        if (cudaMemcpyAsync(Sx_out, c->Sx, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            fnn::set_error("fnn_rowsums: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = FNN_E_CUDA;
+        }
+    }
+    fnn_ctx_destroy(c);
+    return rc;
+}
+
+// internal accessors for the other translation units of the library (not part of the ABI)
+int64_t fnn_ctx_n_(fnn_ctx* c) { return c->n; }
+void fnn_ctx_mark_loaded_(fnn_ctx* c) { c->loaded = true; }

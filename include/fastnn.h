@@ -1,0 +1,111 @@
+/* fastnn.h — C ABI of libfastnn.so, the B200-native Neighbor-Net hot path.
+ *
+ * Drop-in boundary for JacobPorter/FastNeighborNet (pure Java, no FFI of its own): the two
+ * seams a maintainer re-points through JNI are
+ *   B1  ordering       FastNN.java:326-361 (new NeighborNet{Canonical,Local,Random}(D, nTaxa, ...))
+ *                      + FastNN.java:378/391 (int[] ordering = myNMO.runNeighborNet()),
+ *                      implemented by NetMakerOriginal.java:129-162
+ *   B2  split weights  FastNN.java:401-466 (live dense NNLS) / the commented call
+ *                      FastNN.java:509-511 -> CircularSplitWeights.java:67,162
+ * See INTEGRATION.md for the JNI stub.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions: every entry point returns 0 on success or a negative FNN_E_* code and sets
+ * fnn_last_error().  The library never writes to stdout, never throws across the ABI, and
+ * has NO CPU fallback: without a CUDA device (sm_100) every compute call fails with
+ * FNN_E_NODEVICE.  All arithmetic is IEEE binary64 without FMA contraction, in the
+ * reference's summation order, so the circular ordering is bit-exact.
+ */
+#ifndef FASTNN_H
+#define FASTNN_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNN_OK 0
+#define FNN_E_ARG (-1)
+#define FNN_E_NODEVICE (-2)
+#define FNN_E_CUDA (-3)
+#define FNN_E_NOMEM (-4)
+#define FNN_E_STATE (-5)
+#define FNN_E_IO (-6)
+#define FNN_E_UNSUPPORTED (-7)
+
+/* NetMakerOriginal.NMMode (NetMakerOriginal.java:19-21) */
+enum fnn_mode {
+    FNN_CANONICAL = 0,
+    FNN_RELAXED = 1,
+    FNN_RANDOM_N = 2,
+    FNN_RANDOM_NLOGN = 3,
+    FNN_RANDOM_LOGN = 4
+};
+
+/* All knobs of the reference CLI that reach the hot path (FastNN.java:136-172) plus the
+ * hard-coded constants it buries (SURVEY.md §5 "config / flags"). */
+typedef struct fnn_opts {
+    int32_t mode;               /* -mode, enum fnn_mode; default canonical */
+    int32_t mult;               /* -mult, default 5 (NeighborNetRandom.java:47) */
+    int32_t additive;           /* -additive (NeighborNetLocal.java:223) */
+    int32_t canonical_fallback; /* 1024: num_active <= this uses the canonical scan (NetMakerOriginal.java:361) */
+    int64_t seed;               /* java.util.Random(seed) stream for Relaxed/Random (reference is unseedable) */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t use_graph;          /* 1: replay the per-iteration kernel sequence as a CUDA graph */
+    int32_t record_trace;       /* 1: keep the per-iteration (m,c,Cx,Cy,x,y,kind,best) trace on device */
+    int32_t profile_every;      /* >0: time the selection kernel of every k-th iteration with CUDA events */
+    int32_t reserved[6];
+} fnn_opts;
+
+typedef struct fnn_ctx fnn_ctx; /* opaque: device matrix + node tables for one problem of n taxa */
+
+typedef struct fnn_stats {
+    int64_t iterations;        /* agglomeration iterations executed */
+    int64_t kernel_launches;   /* CUDA kernels launched by the last run (graph nodes counted) */
+    int64_t scan_launches;     /* selection-kernel launches */
+    double scan_alg_bytes;     /* sum over iterations of 4*m*(m-1) - 8*pairs + 8*m */
+    double prof_scan_ms;       /* profile_every>0: summed CUDA-event time of the sampled selection launches */
+    double prof_scan_bytes;    /* ... and their algorithmic bytes */
+    int64_t prof_scan_samples;
+    double order_ms;           /* device time of the whole ordering run (CUDA events) */
+    double h2d_ms;             /* device time of the host->device matrix upload, if any */
+    double reserved[8];
+} fnn_stats;
+
+void fnn_default_opts(fnn_opts* o);
+const char* fnn_last_error(void);
+int fnn_device_count(void);
+
+/* ---- context API (device-resident matrix; used by bench `value` and by tests) ---------- */
+int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out);
+void fnn_ctx_destroy(fnn_ctx* c);
+/* upload an n*n row-major symmetric zero-diagonal host matrix (the Java double[][] D of FastNN.java:307-312) */
+int fnn_ctx_load_host(fnn_ctx* c, const double* D_rowmajor);
+/* copy from a device matrix with leading dimension ld_src (elements) */
+int fnn_ctx_load_device(fnn_ctx* c, const double* dD, int64_t ld_src);
+/* synthesise the SURVEY §8(d) additive-tree + noise matrix in device memory from O(n) host parameters
+ * (h[n-1], a[n], slot_of_taxon[n]; see fastneighbornet_b200/synth.py) */
+int fnn_ctx_synth(fnn_ctx* c, const double* h, const double* a, const int64_t* slot_of_taxon, uint64_t noise_base, double eps);
+/* copy the current device matrix back in the original taxon layout (only valid before fnn_ctx_order) */
+int fnn_ctx_read_matrix(fnn_ctx* c, double* D_rowmajor_out);
+/* run NetMakerOriginal.runNeighborNet (NetMakerOriginal.java:129): ordering_out has n+1 entries,
+ * [0]=0, [1]=1, 1-based taxon ids.  The device matrix is consumed (mutated in place like the Java D). */
+int fnn_ctx_order(fnn_ctx* c, int32_t* ordering_out);
+/* per-iteration trace rows of 8 doubles (m, c, Cx.id, Cy.id, x.id, y.id, kind, best); returns rows written */
+int64_t fnn_ctx_trace(fnn_ctx* c, double* rows_out, int64_t max_rows);
+int fnn_ctx_stats(fnn_ctx* c, fnn_stats* out);
+/* device pointer + leading dimension of the internal matrix (for zero-copy producers such as torch) */
+int fnn_ctx_matrix_ptr(fnn_ctx* c, double** dptr, int64_t* ld);
+
+/* ---- one-shot seams ----------------------------------------------------------------- */
+/* B1: replaces `new NeighborNetX(D, n, ...).runNeighborNet()`.  Exactly one of D_rowmajor
+ * (host, n*n) or phylip_path must be non-NULL.  n<=3 returns the identity ordering
+ * (NetMakerOriginal.java:133-140). */
+int fnn_order(const fnn_opts* o, const double* D_rowmajor, const char* phylip_path, int64_t n, int32_t* ordering_out);
+
+/* initial cluster row sums only (NetMakerOriginal.initialize, :164-191) — kernel K1, exposed for parity tests */
+int fnn_rowsums(const fnn_opts* o, const double* D_rowmajor, int64_t n, double* Sx_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTNN_H */

@@ -1,0 +1,89 @@
+"""Parity of the CUDA ordering engine (through the C ABI) against the CPU oracle: the circular
+ordering and the whole per-iteration trace (m, c, Cx, Cy, x, y, kind, best) must be bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import integer_matrix, random_matrix, tree_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_gpu(fnn, D, **opts):
+    with fnn.Context(D.shape[0], record_trace=1, **opts) as c:
+        c.load_host(D)
+        o = c.order()
+        return o, c.trace(), c.stats()
+
+
+def _check(fnn, D, **opts):
+    o_ref, tr_ref, _ = oracle.order(D)
+    o, tr, st = _run_gpu(fnn, D, **opts)
+    assert tr.shape == tr_ref.shape, (tr.shape, tr_ref.shape)
+    bad = np.nonzero((tr != tr_ref).any(axis=1))[0]
+    assert bad.size == 0, f"first diverging iteration {bad[0]}: gpu={tr[bad[0]]} ref={tr_ref[bad[0]]}"
+    assert (o == o_ref).all()
+    return st
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7, 8, 9, 12, 17, 33, 64, 100])
+@pytest.mark.parametrize("kind", ["tree0", "tree", "int", "rand"])
+def test_small(fnn, n, kind):
+    for seed in (1, 2, 3):
+        D = {"tree0": lambda: tree_matrix(n, seed, 0.0), "tree": lambda: tree_matrix(n, seed, 0.05),
+             "int": lambda: integer_matrix(n, seed), "rand": lambda: random_matrix(n, seed)}[kind]()
+        _check(fnn, D)
+
+
+def test_config1_n200(fnn):
+    """BASELINE configs[0]: canonical -order, 200-taxon additive tree (eps=0)."""
+    _check(fnn, tree_matrix(200, 1, 0.0))
+
+
+@pytest.mark.parametrize("use_graph", [0, 1])
+def test_n1000(fnn, use_graph):
+    _check(fnn, tree_matrix(1000, 2, 0.05), use_graph=use_graph)
+
+
+def test_n1500_ties(fnn):
+    _check(fnn, integer_matrix(1500, 7, hi=4))
+
+
+def test_n3000(fnn):
+    st = _check(fnn, tree_matrix(3000, 3, 0.05))
+    assert st["iterations"] >= 2997
+
+
+def test_rowsums(fnn):
+    D = tree_matrix(777, 5)
+    assert (fnn.rowsums(D) == oracle.rowsums(D)).all()
+
+
+def test_small_n_identity(fnn):
+    for n in (1, 2, 3):
+        assert fnn.order(np.zeros((n, n))).tolist() == list(range(n + 1))
+
+
+def test_device_synth_matches_numpy(fnn):
+    n = 513
+    for eps in (0.0, 0.05):
+        with fnn.Context(n) as c:
+            c.synth(9, eps)
+            D = c.read_matrix()
+        assert (D == tree_matrix(n, 9, eps)).all()
+
+
+def test_reference_style_classes(fnn):
+    D = tree_matrix(300, 11)
+    o_ref, _, _ = oracle.order(D)
+    nn = fnn.NeighborNetCanonical(D, 300, 1, None)
+    assert (nn.runNeighborNet() == o_ref).all()
+
+
+def test_phylip_path(fnn, tmp_path):
+    from fastneighbornet_b200 import synth
+    D = tree_matrix(150, 4)
+    p = tmp_path / "d.phy"
+    synth.write_phylip(str(p), D)
+    o_ref, _, _ = oracle.order(D)
+    assert (fnn.order(phylip_path=str(p), n=150) == o_ref).all()
