@@ -64,6 +64,7 @@ struct DevState {
     int chg_src[MAXK];
     double chg_Sx[MAXK];
     int final3[4];
+    double alg_bytes;             // running sum of the selection scan's algorithmic bytes
 };
 
 struct Partial { double q; unsigned long long key; };
@@ -423,6 +424,7 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
         int cx = p2s[st->sel_i], cy = p2s[st->sel_j];
         if (id[cx] > id[cy]) { int t = cx; cx = cy; cy = t; }
         sh[0] = cx; sh[1] = nbr_of(cx, P2); sh[2] = cy; sh[3] = nbr_of(cy, P2);
+        st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
     }
     __syncthreads();
     const int Cx = sh[0], Cxn = sh[1], Cy = sh[2], Cyn = sh[3];
@@ -1007,6 +1009,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     c->stats.iterations = c->h_st->iter;
     c->stats.kernel_launches = launches;
     c->stats.scan_launches = scans;
+    c->stats.scan_alg_bytes = c->h_st->alg_bytes;
     c->stats.prof_scan_ms = prof_ms;
     c->stats.prof_scan_bytes = prof_bytes;
     c->stats.prof_scan_samples = prof_samples;

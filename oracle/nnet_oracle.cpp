@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -95,6 +96,8 @@ struct Engine {
     int top = 0;
     int64_t npe_would_fire = 0;   // times the shipped -additive loop would have NPE'd (F7)
     int64_t pair_evals = 0;
+    double alg_bytes = 0.0;      // sum over canonical scans of 8 B per cross-cluster entry
+    int threads = 1;             // >1: NeighborNetCanonical's thread-pool partition (NeighborNetCanonical.java:180-206)
     std::vector<TraceRow>* trace = nullptr;
     int status = 0;
 
@@ -150,6 +153,46 @@ struct Engine {
                 }
             }
         }
+    }
+
+    // NeighborNetCanonical.java:180-206 + FindNodesMulti (:50-132): the 1-based triangular pair
+    // index [1, m(m-1)/2] is cut into `threads` equal slices.  The reference merges the slices
+    // through a synchronized strict `<` in thread-completion order (nondeterministic on exact
+    // ties); here slices are merged in slice order with strict `<`, which is the
+    // 1-thread result.  Used only for the timed CPU baseline.
+    void findNodesCanonicalMT(int num_active, int num_clusters) {
+        Cx = Cy = -1;
+        best = 1.7976931348623157e308;
+        const int T = threads;
+        std::vector<int> bx(T, -1), by(T, -1);
+        std::vector<double> bb(T, 1.7976931348623157e308);
+        const int64_t work = (int64_t)num_active * (num_active - 1) / 2;
+        auto slice = [&](int t) {
+            // slice [lo, hi) of the 0-based linear index over (i, j<i), i-major
+            const int64_t lo = work * t / T, hi = work * (t + 1) / T;
+            int i = (int)((1.0 + std::sqrt(1.0 + 8.0 * (double)lo)) / 2.0);
+            while ((int64_t)i * (i - 1) / 2 > lo) --i;
+            while ((int64_t)(i + 1) * i / 2 <= lo) ++i;
+            int j = (int)(lo - (int64_t)i * (i - 1) / 2);
+            int lx = -1, ly = -1; double lb = 1.7976931348623157e308;
+            for (int64_t k = lo; k < hi; ++k) {
+                int p = act[i], q = act[j];
+                if (!(nd[p].nbr >= 0 && nd[nd[p].nbr].id < nd[p].id) &&
+                    !(nd[q].nbr >= 0 && nd[nd[q].nbr].id < nd[q].id) && nd[q].nbr != p) {
+                    double Dpq = clusterDist(p, q);
+                    double Qpq = ((double)num_clusters - 2.0) * Dpq - nd[p].Sx - nd[q].Sx;
+                    if (lx < 0 || Qpq < lb) { lx = p; ly = q; lb = Qpq; }
+                }
+                if (++j == i) { ++i; j = 0; }
+            }
+            bx[t] = lx; by[t] = ly; bb[t] = lb;
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t) pool.emplace_back(slice, t);
+        slice(0);
+        for (auto& th : pool) th.join();
+        for (int t = 0; t < T; ++t)
+            if (bx[t] >= 0 && (Cx < 0 || bb[t] < best)) { Cx = bx[t]; Cy = by[t]; best = bb[t]; }
     }
 
     // ---- Relaxed (NeighborNetLocal.java) -----------------------------------
@@ -558,7 +601,13 @@ struct Engine {
                 if (trace) trace->push_back(tr);
                 break;
             }
-            if (num_active <= fallback || mode == CANONICAL) findNodesDefault(num_active, num_clusters);
+            if (mode == CANONICAL || num_active <= fallback) {
+                int pairs = 0;
+                for (int i = 0; i < num_active; ++i) if (nd[act[i]].nbr >= 0) ++pairs;
+                alg_bytes += 4.0 * (double)num_active * ((double)num_active - 1.0) - 4.0 * (double)pairs + 8.0 * (double)num_active;
+            }
+            if (mode == CANONICAL && threads > 1 && num_active > fallback) findNodesCanonicalMT(num_active, num_clusters);
+            else if (num_active <= fallback || mode == CANONICAL) findNodesDefault(num_active, num_clusters);
             else if (mode == RELAXED) findNodesRelaxed(num_active, num_clusters);
             else findNodesRandom(num_active, num_clusters);
             if (Cx < 0 || Cy < 0) { status = -10; return num_nodes; }
@@ -806,10 +855,11 @@ extern "C" {
 // trace_out: optional [max_trace][8] doubles (m,c,cx,cy,x,y,kind,best); returns rows in *n_trace.
 int oracle_order(int mode, int64_t n, double* D, int64_t seed, int mult, int additive, int fallback,
                  int32_t* ordering, double* trace_out, int64_t max_trace, int64_t* n_trace,
-                 int64_t* counters /* [0]=pair_evals [1]=npe_would_fire */) {
+                 int64_t* counters /* [0]=pair_evals [1]=npe_would_fire */, int threads, double* alg_bytes) {
     Engine e;
     e.n = n; e.D = D; e.mode = mode; e.mult = mult; e.additive = additive != 0; e.fallback = fallback;
     e.rng = JavaRandom(seed);
+    e.threads = threads < 1 ? 1 : threads;
     std::vector<TraceRow> tr;
     if (trace_out) e.trace = &tr;
     int rc = e.run(ordering);
@@ -823,6 +873,7 @@ int oracle_order(int mode, int64_t n, double* D, int64_t seed, int mult, int add
         if (n_trace) *n_trace = (int64_t)tr.size();
     }
     if (counters) { counters[0] = e.pair_evals; counters[1] = e.npe_would_fire; }
+    if (alg_bytes) *alg_bytes = e.alg_bytes;
     return rc;
 }
 
