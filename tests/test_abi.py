@@ -1,0 +1,53 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/fastnn.h declares; without a
+GPU every compute entry point fails loudly (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fastneighbornet_b200 as fnn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    with open(os.path.join(ROOT, "include", "fastnn.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fnn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    lib = fnn.lib()
+    decl = _declared()
+    assert len(decl) >= 15
+    for s in decl:
+        assert hasattr(lib, s), f"{s} declared in include/fastnn.h but not exported"
+    assert sorted(fnn.api.ABI_SYMBOLS) == decl
+
+
+def test_opts_struct_layout():
+    o = fnn.default_opts()
+    assert (o.mode, o.mult, o.additive, o.canonical_fallback, o.seed, o.use_graph) == (0, 5, 0, 1024, 12345, 1)
+
+
+def test_trivial_sizes_need_no_device():
+    # n <= 3: identity ordering (NetMakerOriginal.java:133-140) - pure host logic
+    for n in (1, 2, 3):
+        assert fnn.order(np.zeros((n, n))).tolist() == list(range(n + 1))
+
+
+def test_argument_errors():
+    with pytest.raises(fnn.FastNNError) as e:
+        fnn.order(None, None, n=5)
+    assert e.value.code == -1
+
+
+@pytest.mark.skipif(fnn.device_count() > 0, reason="GPU present")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(fnn.FastNNError) as e:
+        fnn.order(np.zeros((6, 6)))
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    with pytest.raises(fnn.FastNNError):
+        fnn.Context(10)
