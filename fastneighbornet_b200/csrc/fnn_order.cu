@@ -75,6 +75,11 @@ __device__ __forceinline__ bool better(double q, unsigned long long k, double bq
     return (q < bq) || (q == bq && k < bk);
 }
 
+}  // namespace
+#include <cuda.h>
+namespace {
+#include "fnn_scan_tma.cuh"
+
 // ------------------------------------------------------------------ init kernels
 __global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -720,12 +725,16 @@ struct fnn_ctx {
     Partial* partials = nullptr;
     int scan_grid = 0, row_grid = 0;
     DevState* h_st = nullptr;  // pinned
+    CUtensorMap tmap;
+    bool have_tmap = false;
     cudaGraphExec_t graph = nullptr;
     int graph_iters = 0;
     bool loaded = false;
     fnn_stats stats{};
     int64_t trace_rows = 0;
 };
+
+static int make_tensor_map(fnn_ctx* c);
 
 static int ensure_device(const fnn_opts* o) {
     int cnt = 0;
@@ -814,6 +823,12 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     FNN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     FNN_CUDA(cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 4 * CH_TILE * sizeof(double))));
     FNN_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 1 * CH_TILE * sizeof(double))));
+    c->scan_grid = std::max(c->scan_grid, c->sms);
+    if (o->reserved[0] == 0) {  // reserved[0] = 1 selects the register-tiled scan (A/B only)
+        int trc = make_tensor_map(c);
+        if (trc) { fnn_ctx_destroy(c); return trc; }
+        FNN_CUDA(cudaFuncSetAttribute(tma::k_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma::SMEM_BYTES));
+    }
     *out = c;
     return FNN_OK;
 }
@@ -870,7 +885,31 @@ extern "C" int fnn_ctx_matrix_ptr(fnn_ctx* c, double** dptr, int64_t* ld) {
 }
 
 static inline void launch_scan(fnn_ctx* c) {
-    k_scan<32><<<c->scan_grid, SCAN_THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->partials);
+    if (c->have_tmap)
+        tma::k_scan_tma<<<c->sms, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials);
+    else
+        k_scan<32><<<c->scan_grid, SCAN_THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->partials);
+}
+
+// 2-D tiled tensor map over the n x ld matrix: box = 256 columns x 8 rows, no swizzle, zero OOB fill
+static int make_tensor_map(fnn_ctx* c) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FNN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { fnn::set_error("cuTensorMapEncodeTiled not available"); return FNN_E_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)c->ld, (cuuint64_t)c->n};
+    cuuint64_t gstr[1] = {(cuuint64_t)c->ld * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)tma::BOX_W, (cuuint32_t)tma::BOX_R};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((EncodeFn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, c->D, gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fnn::set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return FNN_E_CUDA; }
+    c->have_tmap = true;
+    return FNN_OK;
 }
 static inline void launch_rest(fnn_ctx* c) {
     k_pick<<<1, PICK_THREADS, 2 * 4 * CH_TILE * sizeof(double), c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st,
