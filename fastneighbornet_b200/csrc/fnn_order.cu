@@ -64,6 +64,7 @@ struct DevState {
     int chg_src[MAXK];
     double chg_Sx[MAXK];
     int final3[4];
+    double Dmax;                  // max |D| at load time (slack of the scan's filter, fnn_scan_tma.cuh)
     double alg_bytes;             // running sum of the selection scan's algorithmic bytes
 };
 
@@ -92,17 +93,19 @@ __global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st) {
 
 // K1: Sx[k] = sum_{j != k} D[k][j], ascending j (NetMakerOriginal.java:164-191).  Thread k walks
 // column k (== row k by symmetry) so that a warp reads 256 contiguous bytes per step.
-__global__ void k_rowsum(const double* __restrict__ D, int64_t ld, int n, double* Sx) {
+__global__ void k_rowsum(const double* __restrict__ D, int64_t ld, int n, double* Sx, DevState* st) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    double s = 0.0;
+    double s = 0.0, mx = 0.0;
     const double* col = D + k;
 #pragma unroll 8
     for (int j = 0; j < n; ++j) {
         double v = col[(int64_t)j * ld];
-        if (j != k) s += v;
+        if (j != k) { s += v; mx = fmax(mx, fabs(v)); }
     }
     Sx[k] = s;
+    // non-negative doubles order like their bit patterns
+    if (st) atomicMax(reinterpret_cast<unsigned long long*>(&st->Dmax), (unsigned long long)__double_as_longlong(mx));
 }
 
 __global__ void k_zero_diag(double* D, int64_t ld, int n) {
@@ -962,7 +965,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     FNN_CUDA(cudaEventRecord(e0, c->stream));
     const int ni = (int)n;
     k_init_nodes<<<(ni + 255) / 256, 256, 0, c->stream>>>(ni, c->id, c->pos, c->p2s, c->st);
-    k_rowsum<<<(ni + 127) / 128, 128, 0, c->stream>>>(c->D, c->ld, ni, c->Sx);
+    k_rowsum<<<(ni + 127) / 128, 128, 0, c->stream>>>(c->D, c->ld, ni, c->Sx, c->st);
     FNN_CUDA(cudaGetLastError());
     int64_t launches = 2, scans = 0;
     const int64_t max_iters = n;  // n-3 .. n-1 iterations; kernels no-op once done
@@ -1078,7 +1081,7 @@ extern "C" int fnn_rowsums(const fnn_opts* o, const double* Dh, int64_t n, doubl
     if (rc) return rc;
     rc = fnn_ctx_load_host(c, Dh);
     if (!rc) {
-        k_rowsum<<<((int)n + 127) / 128, 128, 0, c->stream>>>(c->D, c->ld, (int)n, c->Sx);
+        k_rowsum<<<((int)n + 127) / 128, 128, 0, c->stream>>>(c->D, c->ld, (int)n, c->Sx, nullptr);
         if (cudaMemcpyAsync(Sx_out, c->Sx, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) {
             fnn::set_error("fnn_rowsums: %s", cudaGetErrorString(cudaGetLastError()));

@@ -11,10 +11,13 @@
 
 namespace tma {
 
-constexpr int CONSUMERS = 256;              // 8 consumer warps
+constexpr int NGROUPS = 2;                  // consumer groups; group g owns rows [g*RPG, (g+1)*RPG) of every chunk
+constexpr int GROUP = 256;                  // threads per group: one 16-byte column pair each
+constexpr int CONSUMERS = GROUP * NGROUPS;  // 16 consumer warps
 constexpr int THREADS = CONSUMERS + 32;     // + 1 producer warp
 constexpr int BOX_W = 256;                  // TMA box: 256 columns (2 KB) ...
 constexpr int BOX_R = 8;                    // ... x 8 rows
+constexpr int RPG = BOX_R / NGROUPS;        // rows per consumer group per chunk (even)
 constexpr int TILE_COLS = 2 * BOX_W;        // 512 columns = 2 boxes per stage
 constexpr int TILE_ROWS = 32;               // rows per tile = 4 chunks
 constexpr int STAGES = 6;
@@ -82,12 +85,122 @@ struct __align__(16) RowData { double S; long long pos; };   // one LDS.128 per 
         if (better((QV), key_, bq, bk)) { bq = (QV); bk = key_; }                                        \
     }
 
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// Interior evaluators: "filter, then verify".  The hot loop evaluates a role-free approximation
+// q~ = fma(c-2, Dpq~, -Sx[row]) - Sx[col] (fixed summation order, FMA allowed) and only tests
+// q~ <= best + delta, where delta bounds |q~ - q| for the exactly rounded, role-ordered q of the
+// reference (delta = 16*2^-53 * (3c+2) * max|D|).  Groups that pass are re-walked
+// with the exact arithmetic and the (Q, i, j) key, so the result is bit-identical to evaluating
+// every entry exactly; on non-degenerate data the verify branch is taken a handful of times.
+__device__ __forceinline__ void exact1(double e, const RowData r, double cm2, double cS, int cP, double& bq,
+                                       unsigned long long& bk) {
+    const int rp = (int)r.pos;
+    const bool rowP = rp > cP;
+    const double q = (cm2 * e - (rowP ? r.S : cS)) - (rowP ? cS : r.S);
+    FNN_CONSIDER(q, rp, cP, rowP)
+}
+__device__ __forceinline__ void exact_pp(double2 e0, double2 e1, const RowData r, double cm2, double cS, int cP, double& bq,
+                                         unsigned long long& bk) {
+    const int rp = (int)r.pos;
+    const bool rowP = rp > cP;
+    const double dpq = (((e0.x + (rowP ? e0.y : e1.x)) + (rowP ? e1.x : e0.y)) + e1.y) * 0.25;
+    const double q = (cm2 * dpq - (rowP ? r.S : cS)) - (rowP ? cS : r.S);
+    FNN_CONSIDER(q, rp, cP, rowP)
+}
+
+// OR of (q[k] <= bound) as one chained DSETP per value (nvcc would otherwise rewrite the OR of
+// compares into a tree of emulated fp64 minima, ~6 instructions each).
+__device__ __forceinline__ bool any_le8(const double* q, double b) {
+    int r;
+    asm("{\n.reg .pred p;\n"
+        "setp.le.f64 p, %1, %9;\n setp.le.or.f64 p, %2, %9, p;\n setp.le.or.f64 p, %3, %9, p;\n setp.le.or.f64 p, %4, %9, p;\n"
+        "setp.le.or.f64 p, %5, %9, p;\n setp.le.or.f64 p, %6, %9, p;\n setp.le.or.f64 p, %7, %9, p;\n setp.le.or.f64 p, %8, %9, p;\n"
+        "selp.s32 %0, 1, 0, p;\n}"
+        : "=r"(r) : "d"(q[0]), "d"(q[1]), "d"(q[2]), "d"(q[3]), "d"(q[4]), "d"(q[5]), "d"(q[6]), "d"(q[7]), "d"(b));
+    return r != 0;
+}
+__device__ __forceinline__ bool any_le4(const double* q, double b) {
+    int r;
+    asm("{\n.reg .pred p;\n"
+        "setp.le.f64 p, %1, %5;\n setp.le.or.f64 p, %2, %5, p;\n setp.le.or.f64 p, %3, %5, p;\n setp.le.or.f64 p, %4, %5, p;\n"
+        "selp.s32 %0, 1, 0, p;\n}"
+        : "=r"(r) : "d"(q[0]), "d"(q[1]), "d"(q[2]), "d"(q[3]), "d"(b));
+    return r != 0;
+}
+__device__ __forceinline__ bool any_le2(const double* q, double b) {
+    int r;
+    asm("{\n.reg .pred p;\n setp.le.f64 p, %1, %3;\n setp.le.or.f64 p, %2, %3, p;\n selp.s32 %0, 1, 0, p;\n}"
+        : "=r"(r) : "d"(q[0]), "d"(q[1]), "d"(b));
+    return r != 0;
+}
+
+__device__ __forceinline__ void eval_ss(const double* sm, const RowData* rd, double cm2, double cS0, double cS1, int cP0,
+                                        int cP1, double delta, double& bq, double& bqd, unsigned long long& bk) {
+    static_assert(RPG == 4, "any_le helpers are written for 4 rows per group");
+    double q[2 * RPG];
+#pragma unroll
+    for (int u = 0; u < RPG; ++u) {
+        const double2 e = lds2(sm + u * BOX_W);
+        const double nS = -rd[u].S;
+        q[2 * u] = __fma_rn(cm2, e.x, nS) - cS0;
+        q[2 * u + 1] = __fma_rn(cm2, e.y, nS) - cS1;
+    }
+    if (any_le8(q, bqd)) {
+#pragma unroll
+        for (int u = 0; u < RPG; ++u) {
+            const double2 e = lds2(sm + u * BOX_W);
+            exact1(e.x, rd[u], cm2, cS0, cP0, bq, bk);
+            exact1(e.y, rd[u], cm2, cS1, cP1, bq, bk);
+        }
+        bqd = bq + delta;
+    }
+}
+
+__device__ __forceinline__ void eval_sp(const double* sm, const RowData* rd, double cm2, double cS0, int cP0, double delta,
+                                        double& bq, double& bqd, unsigned long long& bk) {
+    double q[RPG];
+    const double h = cm2 * 0.5;
+#pragma unroll
+    for (int u = 0; u < RPG; ++u) {
+        const double2 e = lds2(sm + u * BOX_W);
+        q[u] = __fma_rn(h, e.x + e.y, -rd[u].S) - cS0;
+    }
+    if (any_le4(q, bqd)) {
+#pragma unroll
+        for (int u = 0; u < RPG; ++u) {
+            const double2 e = lds2(sm + u * BOX_W);
+            exact1((e.x + e.y) * 0.5, rd[u], cm2, cS0, cP0, bq, bk);
+        }
+        bqd = bq + delta;
+    }
+}
+
+__device__ __forceinline__ void eval_pp(const double* sm, const RowData* rd, double cm2, double cS0, int cP0, double delta,
+                                        double& bq, double& bqd, unsigned long long& bk) {
+    double q[RPG / 2];
+    const double h = cm2 * 0.25;
+#pragma unroll
+    for (int u = 0; u < RPG; u += 2) {
+        const double2 e0 = lds2(sm + u * BOX_W);
+        const double2 e1 = lds2(sm + (u + 1) * BOX_W);
+        q[u / 2] = __fma_rn(h, (e0.x + e0.y) + (e1.x + e1.y), -rd[u].S) - cS0;
+    }
+    if (any_le2(q, bqd)) {
+#pragma unroll
+        for (int u = 0; u < RPG; u += 2)
+            exact_pp(lds2(sm + u * BOX_W), lds2(sm + (u + 1) * BOX_W), rd[u], cm2, cS0, cP0, bq, bk);
+        bqd = bq + delta;
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ Sx, const int* __restrict__ pos,
            DevState* st, Partial* partials) {
     if (st->done) return;
     extern __shared__ __align__(1024) unsigned char smem[];
-    double* ring = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    // keep the ring pointer in the shared window (no generic-address loads): offset, not integer cast
+    double* ring = reinterpret_cast<double*>(smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u));
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
     __shared__ RowData rowdata[2][TILE_ROWS];
     __shared__ Partial wbest[THREADS / 32];
@@ -105,6 +218,9 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
 
     double bq = INFINITY;
     unsigned long long bk = ~0ull;
+    // filter slack: bounds the rounding difference between the role-free q~ and the exact q
+    const double delta = 16.0 * 1.1102230246251565e-16 * (3.0 * (double)st->c + 2.0) * st->Dmax;
+    double bqd = INFINITY;
 
     if (tid >= CONSUMERS) {
         // ===================== producer warp: one lane issues the TMA loads =====================
@@ -131,13 +247,15 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
         // ===================== consumer warps =====================
         int stage = 0;
         uint32_t phase = 0;
-        const int box = tid >> 7, lc = (tid & 127) * 2;   // which box of the stage, local column
+        const int grp = tid / GROUP, gt = tid % GROUP;
+        const int box = gt >> 7, lc = (gt & 127) * 2;   // which box of the stage, local column
+        const int uo = grp * RPG;                       // first chunk row of this group
         int tileParity = 0;
         for (TileIter it(m, blockIdx.x, gridDim.x); it.valid(); it.next(), tileParity ^= 1) {
             int r0, cb0;
             it.decode(r0, cb0);
             const int rEnd = min(r0 + TILE_ROWS, m);
-            if (tid < TILE_ROWS && r0 + tid < m) {
+            if (tid < TILE_ROWS && r0 + tid < m) {   // stage the tile's row data
                 rowdata[tileParity][tid].S = Sx[r0 + tid];
                 rowdata[tileParity][tid].pos = pos[r0 + tid];
             }
@@ -151,121 +269,71 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
                 if (c0 + 1 < m) { cS1 = Sx[c0 + 1]; cP1 = pos[c0 + 1]; }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
-            const RowData* rd = rowdata[tileParity];
 
             for (int rc = r0; rc < rEnd; rc += BOX_R) {
                 const int rcEnd = min(rc + BOX_R, rEnd);
                 mbar_wait(&full_bar[stage], phase);
-                const double* sm = ring + (size_t)stage * (STAGE_BYTES / 8) + box * (BOX_R * BOX_W) + lc;
-                if (cvalid && c0 < rcEnd - 1) {
+                const double* sm = ring + (size_t)stage * (STAGE_BYTES / 8) + box * (BOX_R * BOX_W) + lc + uo * BOX_W;
+                const int ra = rc + uo, rb = min(ra + RPG, rcEnd);   // this group's rows of the chunk
+                const RowData* rd = &rowdata[tileParity][ra - r0];
+                if (cvalid && c0 < rb - 1) {
                     const bool full_rows = (rcEnd - rc == BOX_R);
-                    if (colPair) {
-                        if (full_rows && rcEnd <= P2 && c0 < rc) {
-                            // ---- pair rows x pair column, interior
-#pragma unroll
-                            for (int u = 0; u < BOX_R; u += 2) {
-                                const double2 e0 = *reinterpret_cast<const double2*>(sm + u * BOX_W);
-                                const double2 e1 = *reinterpret_cast<const double2*>(sm + (u + 1) * BOX_W);
-                                const RowData r = rd[rc - r0 + u];
-                                const int rp = (int)r.pos;
-                                const bool rowP = rp > cP0;
-                                const double t1 = rowP ? e0.y : e1.x;
-                                const double t2 = rowP ? e1.x : e0.y;
-                                const double dpq = (((e0.x + t1) + t2) + e1.y) * 0.25;
-                                const double s1 = rowP ? r.S : cS0;
-                                const double s2 = rowP ? cS0 : r.S;
-                                const double q = (cm2 * dpq - s1) - s2;
-                                FNN_CONSIDER(q, rp, cP0, rowP)
-                            }
-                        } else if (full_rows && rc >= P2) {
-                            // ---- single rows x pair column (always below the diagonal)
-#pragma unroll
-                            for (int u = 0; u < BOX_R; ++u) {
-                                const double2 e = *reinterpret_cast<const double2*>(sm + u * BOX_W);
-                                const RowData r = rd[rc - r0 + u];
-                                const int rp = (int)r.pos;
-                                const bool rowP = rp > cP0;
-                                const double dpq = (e.x + e.y) * 0.5;
-                                const double s1 = rowP ? r.S : cS0;
-                                const double s2 = rowP ? cS0 : r.S;
-                                const double q = (cm2 * dpq - s1) - s2;
-                                FNN_CONSIDER(q, rp, cP0, rowP)
-                            }
-                        } else {
-                            // ---- generic pair column (diagonal / region boundary / ragged end)
-                            for (int rr = rc; rr < rcEnd;) {
-                                const RowData r = rd[rr - r0];
-                                const int rp = (int)r.pos;
-                                const bool rowP = rp > cP0;
-                                const double s1 = rowP ? r.S : cS0;
-                                const double s2 = rowP ? cS0 : r.S;
-                                if (rr < P2) {
-                                    if (c0 < rr) {
-                                        const double2 e0 = *reinterpret_cast<const double2*>(sm + (rr - rc) * BOX_W);
-                                        const double2 e1 = *reinterpret_cast<const double2*>(sm + (rr - rc + 1) * BOX_W);
-                                        const double t1 = rowP ? e0.y : e1.x;
-                                        const double t2 = rowP ? e1.x : e0.y;
-                                        const double dpq = (((e0.x + t1) + t2) + e1.y) * 0.25;
-                                        const double q = (cm2 * dpq - s1) - s2;
-                                        FNN_CONSIDER(q, rp, cP0, rowP)
-                                    }
-                                    rr += 2;
-                                } else {
-                                    const double2 e = *reinterpret_cast<const double2*>(sm + (rr - rc) * BOX_W);
-                                    const double dpq = (e.x + e.y) * 0.5;
+                    if (colPair && full_rows && rcEnd <= P2 && c0 < ra) {
+                        // ---- pair rows x pair column, interior
+                        eval_pp(sm, rd, cm2, cS0, cP0, delta, bq, bqd, bk);
+                    } else if (colPair && full_rows && rc >= P2) {
+                        // ---- single rows x pair column (always below the diagonal)
+                        eval_sp(sm, rd, cm2, cS0, cP0, delta, bq, bqd, bk);
+                    } else if (!colPair && full_rows && rc >= P2 && c0 + 1 < ra && c0 + 1 < m) {
+                        // ---- single rows x two single columns, interior
+                        eval_ss(sm, rd, cm2, cS0, cS1, cP0, cP1, delta, bq, bqd, bk);
+                    } else if (colPair) {
+                        // ---- generic pair column (diagonal / region boundary / ragged end)
+                        for (int rr = ra; rr < rb;) {
+                            const RowData r = rd[rr - ra];
+                            const int rp = (int)r.pos;
+                            const bool rowP = rp > cP0;
+                            const double s1 = rowP ? r.S : cS0;
+                            const double s2 = rowP ? cS0 : r.S;
+                            if (rr < P2) {
+                                if (c0 < rr) {
+                                    const double2 e0 = lds2(sm + (rr - ra) * BOX_W);
+                                    const double2 e1 = lds2(sm + (rr - ra + 1) * BOX_W);
+                                    const double t1 = rowP ? e0.y : e1.x;
+                                    const double t2 = rowP ? e1.x : e0.y;
+                                    const double dpq = (((e0.x + t1) + t2) + e1.y) * 0.25;
                                     const double q = (cm2 * dpq - s1) - s2;
                                     FNN_CONSIDER(q, rp, cP0, rowP)
-                                    rr += 1;
                                 }
+                                rr += 2;
+                            } else {
+                                const double2 e = lds2(sm + (rr - ra) * BOX_W);
+                                const double dpq = (e.x + e.y) * 0.5;
+                                const double q = (cm2 * dpq - s1) - s2;
+                                FNN_CONSIDER(q, rp, cP0, rowP)
+                                rr += 1;
                             }
                         }
                     } else {
-                        if (full_rows && rc >= P2 && c0 + 1 < rc && c0 + 1 < m) {
-                            // ---- single rows x two single columns, interior
-#pragma unroll
-                            for (int u = 0; u < BOX_R; ++u) {
-                                const double2 e = *reinterpret_cast<const double2*>(sm + u * BOX_W);
-                                const RowData r = rd[rc - r0 + u];
-                                const int rp = (int)r.pos;
-                                {
-                                    const bool rowP = rp > cP0;
-                                    const double s1 = rowP ? r.S : cS0;
-                                    const double s2 = rowP ? cS0 : r.S;
-                                    const double q = (cm2 * e.x - s1) - s2;
-                                    FNN_CONSIDER(q, rp, cP0, rowP)
-                                }
-                                {
-                                    const bool rowP = rp > cP1;
-                                    const double s1 = rowP ? r.S : cS1;
-                                    const double s2 = rowP ? cS1 : r.S;
-                                    const double q = (cm2 * e.y - s1) - s2;
-                                    FNN_CONSIDER(q, rp, cP1, rowP)
-                                }
+                        // ---- generic single columns
+                        for (int rr = max(max(ra, P2), c0 + 1); rr < rb; ++rr) {
+                            const double2 e = lds2(sm + (rr - ra) * BOX_W);
+                            const RowData r = rd[rr - ra];
+                            const int rp = (int)r.pos;
+                            {
+                                const bool rowP = rp > cP0;
+                                const double q = (cm2 * e.x - (rowP ? r.S : cS0)) - (rowP ? cS0 : r.S);
+                                FNN_CONSIDER(q, rp, cP0, rowP)
                             }
-                        } else {
-                            // ---- generic single columns
-                            for (int rr = max(max(rc, P2), c0 + 1); rr < rcEnd; ++rr) {
-                                const double2 e = *reinterpret_cast<const double2*>(sm + (rr - rc) * BOX_W);
-                                const RowData r = rd[rr - r0];
-                                const int rp = (int)r.pos;
-                                {
-                                    const bool rowP = rp > cP0;
-                                    const double s1 = rowP ? r.S : cS0;
-                                    const double s2 = rowP ? cS0 : r.S;
-                                    const double q = (cm2 * e.x - s1) - s2;
-                                    FNN_CONSIDER(q, rp, cP0, rowP)
-                                }
-                                if (c0 + 1 < rr) {
-                                    const bool rowP = rp > cP1;
-                                    const double s1 = rowP ? r.S : cS1;
-                                    const double s2 = rowP ? cS1 : r.S;
-                                    const double q = (cm2 * e.y - s1) - s2;
-                                    FNN_CONSIDER(q, rp, cP1, rowP)
-                                }
+                            if (c0 + 1 < rr) {
+                                const bool rowP = rp > cP1;
+                                const double q = (cm2 * e.y - (rowP ? r.S : cS1)) - (rowP ? cS1 : r.S);
+                                FNN_CONSIDER(q, rp, cP1, rowP)
                             }
                         }
                     }
                 }
+                bqd = bq + delta;
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
