@@ -17,5 +17,6 @@ from .api import (  # noqa: F401
     lib_path,
     order,
     rowsums,
+    seq_sum,
 )
 from . import synth  # noqa: F401

@@ -58,7 +58,7 @@ MODES = {"canonical": 0, "relaxed": 1, "random_n": 2, "random_nlogn": 3, "random
 ABI_SYMBOLS = [
     "fnn_default_opts", "fnn_last_error", "fnn_device_count", "fnn_ctx_create", "fnn_ctx_destroy",
     "fnn_ctx_load_host", "fnn_ctx_load_device", "fnn_ctx_synth", "fnn_ctx_read_matrix", "fnn_ctx_order",
-    "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums",
+    "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums", "fnn_seq_sum",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
         L.fnn_ctx_matrix_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
         L.fnn_order.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
         L.fnn_rowsums.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int64, c_dp]
+        L.fnn_seq_sum.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int32, ctypes.c_int64, c_dp]
         _LIB = L
     return _LIB
 
@@ -211,6 +212,16 @@ def rowsums(D, **opts):
     o = default_opts(**opts)
     out = np.zeros(D.shape[0], dtype=np.float64)
     _check(lib().fnn_rowsums(ctypes.byref(o), _dp(D), D.shape[0], _dp(out)))
+    return out
+
+
+def seq_sum(rows, serial=False, **opts):
+    """Left-to-right fp64 sums of up to 4 equally long rows on the device (fnn_seq_sum)."""
+    rows = np.ascontiguousarray(np.atleast_2d(rows), dtype=np.float64)
+    o = default_opts(**opts)
+    o.reserved[1] = 1 if serial else 0
+    out = np.zeros(rows.shape[0], dtype=np.float64)
+    _check(lib().fnn_seq_sum(ctypes.byref(o), _dp(rows), rows.shape[0], rows.shape[1], _dp(out)))
     return out
 
 

@@ -80,6 +80,7 @@ __device__ __forceinline__ bool better(double q, unsigned long long k, double bq
 #include <cuda.h>
 namespace {
 #include "fnn_scan_tma.cuh"
+#include "fnn_exact_sum.cuh"
 
 // ------------------------------------------------------------------ init kernels
 __global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st) {
@@ -388,9 +389,10 @@ __device__ __forceinline__ double duv_rule(bool uFirst, double dZX, double dYX, 
 constexpr int PICK_THREADS = 1024;
 
 __global__ void __launch_bounds__(PICK_THREADS, 1)
-k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState* st, int* amalg, double* trace) {
+k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState* st, int* amalg, double* trace, int serial_chain) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[4][CH_TILE] = reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw);
+    __shared__ xsum::Smem xs;
     __shared__ int sh[8];
     __shared__ double rx[4];
     if (st->done) return;
@@ -448,7 +450,8 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
             const bool full = (s >= P2) || s == Cx || s == Cxn || s == Cy || s == Cyn;
             return full ? v : v * 0.5;
         };
-        block_seq_sum<4>(buf, m, load, rx);
+        if (serial_chain) block_seq_sum<4>(buf, m, load, rx);
+        else xsum::block_exact_seq_sum<4>(reinterpret_cast<double (*)[xsum::TILE]>(smem_raw), &xs, m, load, rx);
     } else {
         if (tid < 4) rx[tid] = 0.0;
         __syncthreads();
@@ -689,14 +692,16 @@ k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevSta
 
 // ------------------------------------------------------------------ K6b: u.Sx chain + commit
 __global__ void __launch_bounds__(PICK_THREADS, 1)
-k_chain(double* Sx, const int* id, const int* p2s, DevState* st, const double* __restrict__ stage) {
+k_chain(double* Sx, const int* id, const int* p2s, DevState* st, const double* __restrict__ stage, int serial_chain) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[1][CH_TILE] = reinterpret_cast<double (*)[1][CH_TILE]>(smem_raw);
+    __shared__ xsum::Smem xs;
     __shared__ double tot[1];
     if (st->done || st->skip) return;
     const int m_new = st->m_new;
     auto load = [&](int, int i) -> double { return stage[i]; };
-    block_seq_sum<1>(buf, m_new, load, tot);
+    if (serial_chain) block_seq_sum<1>(buf, m_new, load, tot);
+    else xsum::block_exact_seq_sum<1>(reinterpret_cast<double (*)[xsum::TILE]>(smem_raw), &xs, m_new, load, tot);
     if (threadIdx.x == 0) {
         const int su = st->su;
         Sx[su] = tot[0];
@@ -708,6 +713,18 @@ k_chain(double* Sx, const int* id, const int* p2s, DevState* st, const double* _
             for (int i = 0; i < 3; ++i) st->final3[i] = id[p2s[i]];
         }
     }
+}
+
+// stand-alone entry for the exact left-to-right summation (parity tests of fnn_exact_sum.cuh)
+__global__ void __launch_bounds__(PICK_THREADS, 1)
+k_seqsum(const double* __restrict__ rows, int64_t stride, int nrows, int len, double* out, int serial_chain) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ xsum::Smem xs;
+    __shared__ double res[4];
+    auto load = [&](int r, int i) -> double { return r < nrows ? rows[(int64_t)r * stride + i] : 0.0; };
+    if (serial_chain) block_seq_sum<4>(reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw), len, load, res);
+    else xsum::block_exact_seq_sum<4>(reinterpret_cast<double (*)[xsum::TILE]>(smem_raw), &xs, len, load, res);
+    if (threadIdx.x < nrows) out[threadIdx.x] = res[threadIdx.x];
 }
 
 }  // namespace
@@ -824,8 +841,8 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     if (o->record_trace) FNN_ALLOC(c->trace, sizeof(double) * 8 * (n + 8));
     FNN_CUDA(cudaMallocHost((void**)&c->h_st, sizeof(DevState)));
     FNN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    FNN_CUDA(cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 4 * CH_TILE * sizeof(double))));
-    FNN_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 1 * CH_TILE * sizeof(double))));
+    FNN_CUDA(cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * xsum::TILE * sizeof(double))));
+    FNN_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1 * xsum::TILE * sizeof(double))));
     c->scan_grid = std::max(c->scan_grid, c->sms);
     if (o->reserved[0] == 0) {  // reserved[0] = 1 selects the register-tiled scan (A/B only)
         int trc = make_tensor_map(c);
@@ -887,6 +904,10 @@ extern "C" int fnn_ctx_matrix_ptr(fnn_ctx* c, double** dptr, int64_t* ld) {
     return FNN_OK;
 }
 
+constexpr size_t PICK_SMEM = 4 * xsum::TILE * sizeof(double);   // >= 2*4*CH_TILE doubles of the serial variant
+constexpr size_t CHAIN_SMEM = 1 * xsum::TILE * sizeof(double);
+static_assert(PICK_THREADS == xsum::THREADS, "exact-sum block size");
+
 static inline void launch_scan(fnn_ctx* c) {
     if (c->have_tmap)
         tma::k_scan_tma<<<c->sms, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials);
@@ -915,11 +936,11 @@ static int make_tensor_map(fnn_ctx* c) {
     return FNN_OK;
 }
 static inline void launch_rest(fnn_ctx* c) {
-    k_pick<<<1, PICK_THREADS, 2 * 4 * CH_TILE * sizeof(double), c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st,
-                                                                            c->amalg, c->trace);
+    k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
+                                                    c->o.reserved[1] != 2);
     k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
     k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage);
-    k_chain<<<1, PICK_THREADS, 2 * 1 * CH_TILE * sizeof(double), c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage);
+    k_chain<<<1, PICK_THREADS, CHAIN_SMEM, c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage, c->o.reserved[1] != 2);
 }
 
 // expandNodes (NetMakerOriginal.java:246-325) on the host from the amalgamation log
@@ -1095,3 +1116,33 @@ extern "C" int fnn_rowsums(const fnn_opts* o, const double* Dh, int64_t n, doubl
 // internal accessors for the other translation units of the library (not part of the ABI)
 int64_t fnn_ctx_n_(fnn_ctx* c) { return c->n; }
 void fnn_ctx_mark_loaded_(fnn_ctx* c) { c->loaded = true; }
+
+extern "C" int fnn_seq_sum(const fnn_opts* o, const double* rows, int32_t nrows, int64_t len, double* out) {
+    if (!rows || !out || nrows < 1 || nrows > 4 || len < 0 || len > 0x7fffffff) { fnn::set_error("fnn_seq_sum: bad arguments"); return FNN_E_ARG; }
+    int rc = ensure_device(o);
+    if (rc) return rc;
+    double *d_rows = nullptr, *d_out = nullptr;
+    FNN_CUDA(cudaMalloc((void**)&d_rows, sizeof(double) * (size_t)nrows * (size_t)std::max<int64_t>(len, 1)));
+    FNN_CUDA(cudaMalloc((void**)&d_out, sizeof(double) * 4));
+    FNN_CUDA(cudaMemcpy(d_rows, rows, sizeof(double) * (size_t)nrows * (size_t)len, cudaMemcpyHostToDevice));
+    FNN_CUDA(cudaFuncSetAttribute(k_seqsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICK_SMEM));
+    k_seqsum<<<1, PICK_THREADS, PICK_SMEM>>>(d_rows, len, nrows, (int)len, d_out, o ? o->reserved[1] : 0);
+    FNN_CUDA(cudaGetLastError());
+    if (o && o->reserved[2] > 0 && getenv("FNN_DEBUG")) {   // kernel-only timing for profiling sessions
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int i = 0; i < o->reserved[2]; ++i)
+            k_seqsum<<<1, PICK_THREADS, PICK_SMEM>>>(d_rows, len, nrows, (int)len, d_out, o->reserved[1]);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[fnn] k_seqsum nrows=%d len=%lld serial=%d: %.2f us/launch\n", nrows, (long long)len, o->reserved[1],
+                1e3 * ms / o->reserved[2]);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    FNN_CUDA(cudaMemcpy(out, d_out, sizeof(double) * nrows, cudaMemcpyDeviceToHost));
+    cudaFree(d_rows); cudaFree(d_out);
+    return FNN_OK;
+}

@@ -53,7 +53,8 @@ typedef struct fnn_opts {
     int32_t use_graph;          /* 1: replay the per-iteration kernel sequence as a CUDA graph */
     int32_t record_trace;       /* 1: keep the per-iteration (m,c,Cx,Cy,x,y,kind,best) trace on device */
     int32_t profile_every;      /* >0: time the selection kernel of every k-th iteration with CUDA events */
-    int32_t reserved[6];
+    int32_t reserved[6];        /* [0]=1: register-tiled scan instead of the TMA pipeline (A/B); [1]=2: collapse the
+                                   sequential chains with the exact parallel summation (experimental, slower today) */
 } fnn_opts;
 
 typedef struct fnn_ctx fnn_ctx; /* opaque: device matrix + node tables for one problem of n taxa */
@@ -104,6 +105,11 @@ int fnn_order(const fnn_opts* o, const double* D_rowmajor, const char* phylip_pa
 
 /* initial cluster row sums only (NetMakerOriginal.initialize, :164-191) — kernel K1, exposed for parity tests */
 int fnn_rowsums(const fnn_opts* o, const double* D_rowmajor, int64_t n, double* Sx_out);
+
+/* left-to-right fp64 sums of nrows (<=4) rows of length len, bit-identical to `for (i) s += x[i]`
+ * (the accumulation order of ComputeRx / updateClusterDistances, NetMakerOriginal.java:549-561, :530-535),
+ * computed by the parallel exact-summation kernel (csrc/fnn_exact_sum.cuh) - exposed for parity tests */
+int fnn_seq_sum(const fnn_opts* o, const double* rows, int32_t nrows, int64_t len, double* out);
 
 #ifdef __cplusplus
 }
