@@ -18,5 +18,8 @@ from .api import (  # noqa: F401
     order,
     rowsums,
     seq_sum,
+    split_weights,
+    csw_matvec,
+    weighted_splits,
 )
 from . import synth  # noqa: F401

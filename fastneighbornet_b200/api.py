@@ -59,6 +59,7 @@ ABI_SYMBOLS = [
     "fnn_default_opts", "fnn_last_error", "fnn_device_count", "fnn_ctx_create", "fnn_ctx_destroy",
     "fnn_ctx_load_host", "fnn_ctx_load_device", "fnn_ctx_synth", "fnn_ctx_read_matrix", "fnn_ctx_order",
     "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums", "fnn_seq_sum",
+    "fnn_split_weights", "fnn_csw_matvec",
 ]
 
 
@@ -93,6 +94,9 @@ def lib():
         L.fnn_ctx_matrix_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
         L.fnn_order.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
         L.fnn_rowsums.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int64, c_dp]
+        L.fnn_split_weights.argtypes = [ctypes.POINTER(fnn_opts), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64, c_dp,
+                                        ctypes.POINTER(ctypes.c_int64)]
+        L.fnn_csw_matvec.argtypes = [ctypes.POINTER(fnn_opts), ctypes.c_int32, c_dp, ctypes.c_int64, c_dp]
         L.fnn_seq_sum.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int32, ctypes.c_int64, c_dp]
         _LIB = L
     return _LIB
@@ -222,6 +226,46 @@ def seq_sum(rows, serial=False, **opts):
     o.reserved[1] = 1 if serial else 0
     out = np.zeros(rows.shape[0], dtype=np.float64)
     _check(lib().fnn_seq_sum(ctypes.byref(o), _dp(rows), rows.shape[0], rows.shape[1], _dp(out)))
+    return out
+
+
+def split_weights(ordering, d_upper, constrained=True, **opts):
+    """Seam B2 (fnn_split_weights): CircularSplitWeights.getWeights(ntax, ordering, d, v="ols", constrained, ...)
+    (CircularSplitWeights.java:162).  Returns (x[npairs] in the live split indexing, stats dict)."""
+    ordering = np.ascontiguousarray(ordering, dtype=np.int32)
+    n = ordering.shape[0] - 1
+    d_upper = np.ascontiguousarray(d_upper, dtype=np.float64)
+    assert d_upper.shape[0] == n * (n - 1) // 2
+    o = default_opts(**opts)
+    o.reserved[3] = 0 if constrained else 1
+    x = np.zeros_like(d_upper)
+    st = np.zeros(5, dtype=np.int64)
+    _check(lib().fnn_split_weights(ctypes.byref(o), ordering.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _dp(d_upper), n,
+                                   _dp(x), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
+    return x, {"cg_iters": int(st[0]), "cg_calls": int(st[1]), "outer": int(st[2]), "inner": int(st[3]), "kernel_launches": int(st[4])}
+
+
+def csw_matvec(which, v, n, **opts):
+    """which: 'ab' | 'atx' | 'unconstrained' on a packed npairs vector (fnn_csw_matvec)."""
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    o = default_opts(**opts)
+    out = np.zeros_like(v)
+    _check(lib().fnn_csw_matvec(ctypes.byref(o), {"ab": 0, "atx": 1, "unconstrained": 2}[which], _dp(v), int(n), _dp(out)))
+    return out
+
+
+def weighted_splits(ordering, x, cutoff=1e-6):
+    """Split emission of FastNN.java:455-466: keep x > cutoff in (i,j) row-major-upper order; split (i,j) is the taxon
+    set {ordering[i+1..j]}.  Returns a list of (sorted taxon list, weight); sets are built only for kept splits."""
+    n = len(ordering) - 1
+    out = []
+    idx = 0
+    for i in range(n):
+        row = x[idx: idx + (n - 1 - i)]
+        for off in np.nonzero(row > cutoff)[0]:
+            j = i + 1 + int(off)
+            out.append((sorted(int(t) for t in ordering[i + 1: j + 1]), float(row[off])))
+        idx += n - 1 - i
     return out
 
 

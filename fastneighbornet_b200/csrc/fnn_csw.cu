@@ -1,0 +1,637 @@
+// fnn_csw.cu — seam B2: circular split weights (CircularSplitWeights.java) on the B200.
+//
+// Reference algorithm (kept): unconstrained closed form (CircularSplitWeights.java:247-271), then the
+// active-set method with conjugate gradients on A^T A x = A^T d restricted to the free set
+// (:359-557, :769-831), 60 % collapse (:282-330), min-ratio step (:438-460), most-negative
+// active gradient release (:464-555).  W == 1 ("ols", :172-177, :213-236).
+//
+// What changes (B200-first): the two mat-vecs are not the reference's n-1 dependent wavefronts
+// (:603-633, :643-731) but ONE primitive - the 2-D inclusive prefix sum P of the packed upper
+// triangle (a warp-per-row scan, then a thread-per-column scan) - followed by O(1) gathers:
+//     (Ab)(a,b)  = 2P(a-1,b-1) - P(a-1,a-1) + P(b-1,n-1) - P(a-1,n-1) - P(b-1,b-1)
+//     (A^T d)(i,j) = (PRS[j] - PRS[i]) - 2 (G(j,j) - G(i,j)),  G = prefix2d(d), PRS = prefix of row sums
+// Dot products use a fixed two-level tree.  Every summation order here is restated literally
+// by the L1 oracle (oracle/csw_l1.cpp), so the active-set path - and therefore the weights - are
+// bit-identical to it; the distance to the reference's own summation order (L0) is the
+// algorithm's intrinsic noise floor and is reported by the tests.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include "fastnn.h"
+#include "fnn_common.h"
+
+namespace {
+
+struct Scalars {
+    double rho, rho_old, e0sq, alpha, beta, dot;
+    long long k, kmax, iters_total;
+    int done;
+    int pad;
+};
+
+__host__ __device__ inline int64_t row_start(int64_t n, int64_t i) { return i * (2 * n - i - 1) / 2; }
+__host__ __device__ inline int64_t pidx(int64_t n, int64_t i, int64_t j) { return i * (2 * n - i - 3) / 2 + j - 1; }
+
+// ---------------------------------------------------------------- prefix2d: row pass
+// warp per row; blocks of 32 elements scanned Kogge-Stone, carry added sequentially
+__global__ void k_rowscan(const double* __restrict__ v, double* __restrict__ Rw, double* __restrict__ RT, int n,
+                          const int* done) {
+    if (done && *done) return;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int64_t i = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); i < n - 1; i += (int64_t)gridDim.x * wpb) {
+        const int64_t rs = row_start(n, i);
+        const int len = n - 1 - (int)i;
+        double carry = 0.0;
+        for (int blk = 0; blk < len; blk += 32) {
+            double e = (blk + lane < len) ? v[rs + blk + lane] : 0.0;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, e, off);
+                if (lane >= off) e = e + t;
+            }
+            const double out = carry + e;
+            if (blk + lane < len) Rw[rs + blk + lane] = out;
+            carry = __shfl_sync(0xffffffffu, out, 31);
+        }
+        if (RT && lane == 0) RT[i] = carry;
+    }
+    if (RT && blockIdx.x == 0 && threadIdx.x == 0) RT[n - 1] = 0.0;
+}
+
+// ---------------------------------------------------------------- prefix2d: column pass (+ raw column sums)
+template <bool WITH_CT>
+__global__ void k_colscan(const double* __restrict__ Rw, const double* __restrict__ v, double* __restrict__ P,
+                          double* __restrict__ CT, int n, const int* done) {
+    if (done && *done) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (j == 0) { if (WITH_CT) CT[0] = 0.0; return; }
+    double acc = 0.0, acc2 = 0.0;
+    int64_t q = j - 1;   // idx(0, j)
+    for (int i = 0; i < j; ++i) {
+        acc = acc + Rw[q];
+        P[q] = acc;
+        if (WITH_CT) acc2 = acc2 + v[q];
+        q += n - i - 2;  // idx(i+1, j) - idx(i, j)
+    }
+    if (WITH_CT) CT[j] = acc2;
+}
+
+__global__ void k_prs(const double* RT, const double* CT, double* PRS, int n, const int* done) {
+    if (done && *done) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double acc = 0.0;
+    for (int a = 0; a < n; ++a) { acc = acc + (RT[a] + CT[a]); PRS[a] = acc; }
+}
+
+// ---------------------------------------------------------------- fixed reduction tree (level 1 inside producers)
+// 256 threads own 4 consecutive values each: ((e0+e1)+e2)+e3, xor-butterfly in the warp, 8 warp totals added in order.
+__device__ __forceinline__ double block_tree_1024(double s, double* sh8) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) sh8[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+        t = sh8[0];
+        for (int w = 1; w < 8; ++w) t = t + sh8[w];
+    }
+    return t;   // valid in thread 0
+}
+
+enum Epilogue { EP_NONE = 0, EP_ALPHA = 1, EP_RHO_STEP = 2, EP_RHO_INIT = 3, EP_E0 = 4 };
+
+__device__ void run_epilogue(int ep, double val, Scalars* sc) {
+    if (ep == EP_ALPHA) { sc->dot = val; sc->alpha = sc->rho / val; }
+    else if (ep == EP_RHO_STEP || ep == EP_RHO_INIT) {
+        if (ep == EP_RHO_STEP) { sc->rho_old = sc->rho; sc->iters_total += 1; }
+        else sc->rho_old = 0.0;
+        sc->rho = val;
+        // loop test of CircularSplitWeights.java:796: while ((rho > e_0*e_0) && (k < kmax))
+        if ((val > sc->e0sq) && (sc->k < sc->kmax)) { sc->k += 1; if (sc->k > 1) sc->beta = val / sc->rho_old; }
+        else sc->done = 1;
+    } else if (ep == EP_E0) {
+        const double e0 = 1e-8 * sqrt(val);   // CG_EPSILON * sqrt(norm(b)), :794
+        sc->e0sq = e0 * e0;
+    } else sc->dot = val;
+}
+
+// level >= 2: one block per 1024 partials; the last level (gridDim.x == 1) runs the epilogue
+__global__ void __launch_bounds__(256) k_tree_level(const double* __restrict__ in, int64_t len, double* __restrict__ out,
+                                                    int ep, Scalars* sc, int gated) {
+    if (gated && sc->done) return;
+    __shared__ double sh8[8];
+    const int64_t base = (int64_t)blockIdx.x * 1024 + 4 * threadIdx.x;
+    double e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e[q] = (base + q < len) ? in[base + q] : 0.0;
+    const double s = ((e[0] + e[1]) + e[2]) + e[3];
+    const double t = block_tree_1024(s, sh8);
+    if (threadIdx.x == 0) {
+        if (gridDim.x == 1) run_epilogue(ep, t, sc);
+        else out[blockIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------- Ab combine: d(a,b) from P
+__global__ void k_ab_combine(const double* __restrict__ P, double* __restrict__ d, int n, const int* done) {
+    if (done && *done) return;
+    const int a = blockIdx.y;
+    if (a >= n - 1) return;
+    const double Pda = (a - 1 >= 1) ? P[pidx(n, a - 2, a - 1)] : 0.0;                 // P(a-1,a-1)
+    const double Prowa = (a >= 1) ? P[pidx(n, a - 1, n - 1)] : 0.0;                    // P(a-1,n-1)
+    for (int b = a + 1 + blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+        const double P1 = (a >= 1) ? P[pidx(n, a - 1, b - 1)] : 0.0;                   // P(a-1,b-1)
+        const double Prowb = P[pidx(n, b - 1, n - 1)];                                  // P(b-1,n-1), b-1 <= n-2
+        const double Pdb = (b - 1 >= 1) ? P[pidx(n, b - 2, b - 1)] : 0.0;              // P(b-1,b-1)
+        double t = 2.0 * P1;
+        t = t - Pda;
+        t = t + Prowb;
+        t = t - Prowa;
+        t = t - Pdb;
+        d[pidx(n, a, b)] = t;
+    }
+}
+
+// ---------------------------------------------------------------- A^T d combine (+ optional mask and fused dot partials)
+// MODE 0: out = p ; MODE 1: out = active ? 0 : p, partial[b] = tree(pvec * out) over this block's 1024 entries
+template <int MODE>
+__global__ void __launch_bounds__(256) k_atx_combine(const double* __restrict__ G, const double* __restrict__ PRS,
+                                                     double* __restrict__ out, int n, int64_t npairs,
+                                                     const unsigned char* __restrict__ active, const double* __restrict__ pvec,
+                                                     double* __restrict__ partial, const int* done) {
+    if (done && *done) return;
+    __shared__ double sh8[8];
+    const int64_t base = (int64_t)blockIdx.x * 1024 + 4 * threadIdx.x;
+    double prod[4] = {0.0, 0.0, 0.0, 0.0};
+    if (base < npairs) {
+        // decode (i, j) of `base`, then walk
+        int64_t i = (int64_t)(((2.0 * n - 1.0) - sqrt((2.0 * n - 1.0) * (2.0 * n - 1.0) - 8.0 * (double)base)) * 0.5);
+        while (i > 0 && row_start(n, i) > base) --i;
+        while (row_start(n, i + 1) <= base) ++i;
+        int64_t j = base - row_start(n, i) + i + 1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t k = base + q;
+            if (k < npairs) {
+                const double u = PRS[j] - PRS[i];
+                const double w = G[pidx(n, j - 1, j)] - G[k];      // G(j,j) - G(i,j); equal operands when i == j-1
+                double pv = u - 2.0 * w;
+                if (MODE == 1) {
+                    if (active[k]) pv = 0.0;
+                    prod[q] = pvec[k] * pv;
+                }
+                out[k] = pv;
+                if (++j == n) { ++i; j = i + 1; }
+            }
+        }
+    }
+    if (MODE == 1) {
+        const double s = ((prod[0] + prod[1]) + prod[2]) + prod[3];
+        const double t = block_tree_1024(s, sh8);
+        if (threadIdx.x == 0) partial[blockIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------- unconstrained closed form (:247-271), one thread per entry
+__global__ void k_unconstrained(const double* __restrict__ d, double* __restrict__ x, int n) {
+    const int i = blockIdx.y;
+    if (i > n - 2) return;
+    const int64_t rs = row_start(n, i);
+    for (int j = i + 1 + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int64_t index = rs + (j - i - 1);
+        double v;
+        if (i == n - 2) v = (d[index] + d[n - 2] - d[n - 3]) / 2.0;                                  // last entry (:270)
+        else if (j == i + 1) v = (d[index] + d[index + (n - i - 2) + 1] - d[index + 1]) / 2.0;       // :250
+        else if (j <= n - 2) v = (d[index] + d[index + (n - i - 2) + 1] - d[index + 1] - d[index + (n - i - 2)]) / 2.0;  // :253
+        else if (i == 0) v = (d[0] + d[n - 2] - d[2 * n - 4]) / 2.0;                                 // :257
+        else v = (d[index] + d[i] - d[i - 1] - d[index + (n - i - 2)]) / 2.0;                        // :259
+        x[index] = v;
+    }
+}
+
+// ---------------------------------------------------------------- CG vector kernels
+// r = active ? 0 : b - r ; partial = tree(r*r)
+__global__ void __launch_bounds__(256) k_residual_init(double* __restrict__ r, const double* __restrict__ b,
+                                                       const unsigned char* __restrict__ active, int64_t len,
+                                                       double* __restrict__ partial) {
+    __shared__ double sh8[8];
+    const int64_t base = (int64_t)blockIdx.x * 1024 + 4 * threadIdx.x;
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (base + q < len) {
+            const double v = active[base + q] ? 0.0 : b[base + q] - r[base + q];
+            r[base + q] = v;
+            e[q] = v * v;
+        }
+    const double t = block_tree_1024(((e[0] + e[1]) + e[2]) + e[3], sh8);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(256) k_square_partials(const double* __restrict__ v, int64_t len, double* __restrict__ partial) {
+    __shared__ double sh8[8];
+    const int64_t base = (int64_t)blockIdx.x * 1024 + 4 * threadIdx.x;
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (base + q < len) e[q] = v[base + q] * v[base + q];
+    const double t = block_tree_1024(((e[0] + e[1]) + e[2]) + e[3], sh8);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+// p = (k == 1) ? r : r + beta * p      (:799-806)
+__global__ void k_pupdate(double* __restrict__ p, const double* __restrict__ r, int64_t len, const Scalars* sc) {
+    if (sc->done) return;
+    const bool first = sc->k == 1;
+    const double beta = sc->beta;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = first ? r[i] : r[i] + beta * p[i];
+}
+// x += alpha p ; r -= alpha w ; partial = tree(r*r)     (:822-828)
+__global__ void __launch_bounds__(256) k_xr_update(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                                                   const double* __restrict__ w, int64_t len, const Scalars* sc,
+                                                   double* __restrict__ partial) {
+    if (sc->done) return;
+    __shared__ double sh8[8];
+    const double alpha = sc->alpha;
+    const int64_t base = (int64_t)blockIdx.x * 1024 + 4 * threadIdx.x;
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (base + q < len) {
+            x[base + q] = x[base + q] + alpha * p[base + q];
+            const double rv = r[base + q] - alpha * w[base + q];
+            r[base + q] = rv;
+            e[q] = rv * rv;
+        }
+    const double t = block_tree_1024(((e[0] + e[1]) + e[2]) + e[3], sh8);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------- active-set helpers
+struct IsNeg { __device__ bool operator()(const double& v) const { return v < 0.0; } };
+
+// (:314-328) x < cutoff -> contract; x == cutoff -> the earliest ties fill the remaining slots
+__global__ void k_mark_below(double* x, unsigned char* active, int64_t len, double cutoff, int* tie_flag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        tie_flag[i] = (v == cutoff) ? 1 : 0;
+        if (v < cutoff) { x[i] = 0.0; active[i] = 1; }
+    }
+}
+__global__ void k_mark_ties(double* x, unsigned char* active, int64_t len, const int* tie_flag, const int* tie_rank, int64_t slots) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        if (tie_flag[i] && tie_rank[i] < slots) { x[i] = 0.0; active[i] = 1; }
+}
+
+struct MinLoc { double v; long long i; };
+struct MinLocOp {
+    __device__ MinLoc operator()(const MinLoc& a, const MinLoc& b) const {
+        if (a.i < 0) return b;
+        if (b.i < 0) return a;
+        return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a;   // first strict minimum in index order
+    }
+};
+// (:438-448) xi = old_x / (old_x - x) over x < 0
+struct RatioIn {
+    const double* x; const double* old_x;
+    __device__ MinLoc operator()(long long i) const {
+        const double xv = x[i];
+        if (xv < 0.0) return MinLoc{old_x[i] / (old_x[i] - xv), i};
+        return MinLoc{0.0, -1};
+    }
+};
+// (:464-479) r = (r - AtWd) * 2 ; min over active
+__global__ void k_gradient(double* r, const double* AtWd, int64_t len) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = r[i] - AtWd[i];
+        r[i] = v * 2.0;
+    }
+}
+struct GradIn {
+    const double* r; const unsigned char* active;
+    __device__ MinLoc operator()(long long i) const { return active[i] ? MinLoc{r[i], i} : MinLoc{0.0, -1}; }
+};
+// (:452-455) old_x += min_xi * (x - old_x) on the free set
+__global__ void k_oldx_step(double* old_x, const double* x, const unsigned char* active, int64_t len, double min_xi) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        if (!active[i]) old_x[i] = old_x[i] + min_xi * (x[i] - old_x[i]);
+}
+__global__ void k_set_one(double* x, unsigned char* active, long long i, double xv, int av, int set_x) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { if (set_x) x[i] = xv; active[i] = (unsigned char)av; }
+}
+__global__ void k_fill(double* v, int64_t len, double val) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) v[i] = val;
+}
+// setupD with the rotated permutation: position 0 <-> ordering[n], position p <-> ordering[p]
+__global__ void k_setup_d(const double* __restrict__ d_upper, const int* __restrict__ ordering, double* __restrict__ d_pos, int n) {
+    const int i = blockIdx.y;
+    if (i > n - 2) return;
+    const int64_t ti = (i == 0 ? ordering[n] : ordering[i]) - 1;
+    for (int j = i + 1 + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int64_t tj = ordering[j] - 1;
+        const int64_t a = ti < tj ? ti : tj, b = ti < tj ? tj : ti;
+        d_pos[pidx(n, i, j)] = d_upper[a * (n - 1) - a * (a - 1) / 2 + b - (a + 1)];   // DistancesAndNames.upperIndex (:24-38)
+    }
+}
+
+// ============================================================================ host driver
+struct Csw {
+    int n = 0;
+    int64_t np = 0, nblk = 0;
+    cudaStream_t st = nullptr;
+    double *d = nullptr, *x = nullptr, *r = nullptr, *w = nullptr, *p = nullptr, *y = nullptr, *old_x = nullptr, *AtWd = nullptr;
+    double *Rw = nullptr, *P = nullptr, *RT = nullptr, *CT = nullptr, *PRS = nullptr, *part1 = nullptr, *part2 = nullptr;
+    unsigned char* active = nullptr;
+    Scalars* sc = nullptr;
+    Scalars* h_sc = nullptr;
+    cudaGraphExec_t cg_graph = nullptr;
+    int64_t cg_calls = 0, outer = 0, inner = 0, launches = 0, launches_per_graph = 0;
+
+    int* done_ptr() { return &sc->done; }
+
+    int alloc() {
+#define CSW_ALLOC(ptr, count) FNN_CUDA(cudaMalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
+        CSW_ALLOC(d, np); CSW_ALLOC(x, np); CSW_ALLOC(r, np); CSW_ALLOC(w, np); CSW_ALLOC(p, np); CSW_ALLOC(y, np);
+        CSW_ALLOC(old_x, np); CSW_ALLOC(AtWd, np); CSW_ALLOC(Rw, np); CSW_ALLOC(P, np);
+        CSW_ALLOC(RT, n); CSW_ALLOC(CT, n); CSW_ALLOC(PRS, n);
+        CSW_ALLOC(part1, nblk + 1); CSW_ALLOC(part2, (nblk + 1023) / 1024 + 1);
+        CSW_ALLOC(active, np); CSW_ALLOC(sc, 1);
+        FNN_CUDA(cudaMallocHost((void**)&h_sc, sizeof(Scalars)));
+        FNN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        FNN_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+        return FNN_OK;
+    }
+    void release() {
+        if (cg_graph) cudaGraphExecDestroy(cg_graph);
+        cudaFree(d); cudaFree(x); cudaFree(r); cudaFree(w); cudaFree(p); cudaFree(y); cudaFree(old_x); cudaFree(AtWd);
+        cudaFree(Rw); cudaFree(P); cudaFree(RT); cudaFree(CT); cudaFree(PRS); cudaFree(part1); cudaFree(part2);
+        cudaFree(active); cudaFree(sc);
+        if (h_sc) cudaFreeHost(h_sc);
+        if (st) cudaStreamDestroy(st);
+    }
+    int grid1d(int64_t len, int threads) const { return (int)std::min<int64_t>((len + threads - 1) / threads, 148 * 16); }
+    dim3 grid_rows() const { return dim3((unsigned)std::max(1, std::min((n + 255) / 256, 64)), (unsigned)(n - 1)); }
+
+    // out = A in   (d = A b)
+    void Ab(const double* in, double* out, const int* gate) {
+        k_rowscan<<<std::min(n, 148 * 8), 256, 0, st>>>(in, Rw, nullptr, n, gate);
+        k_colscan<false><<<(n + 127) / 128, 128, 0, st>>>(Rw, in, P, nullptr, n, gate);
+        k_ab_combine<<<grid_rows(), 256, 0, st>>>(P, out, n, gate);
+        launches += 3;
+    }
+    // G/PRS for A^T in
+    void Atx_prefix(const double* in, const int* gate) {
+        k_rowscan<<<std::min(n, 148 * 8), 256, 0, st>>>(in, Rw, RT, n, gate);
+        k_colscan<true><<<(n + 127) / 128, 128, 0, st>>>(Rw, in, P, CT, n, gate);
+        k_prs<<<1, 32, 0, st>>>(RT, CT, PRS, n, gate);
+        launches += 3;
+    }
+    void Atx(const double* in, double* out, const int* gate) {
+        Atx_prefix(in, gate);
+        k_atx_combine<0><<<(unsigned)nblk, 256, 0, st>>>(P, PRS, out, n, np, nullptr, nullptr, nullptr, gate);
+        launches += 1;
+    }
+    // reduce part1[0..nblk) with the fixed tree, finishing with epilogue ep
+    void finish_tree(int ep, int gated) {
+        const double* in = part1;
+        double* out = part2;
+        int64_t len = nblk;
+        while (true) {
+            const int64_t blocks = (len + 1023) / 1024;
+            k_tree_level<<<(unsigned)blocks, 256, 0, st>>>(in, len, out, ep, sc, gated);
+            launches += 1;
+            if (blocks == 1) break;
+            in = out; out = (out == part2) ? part1 : part2;   // part1 is free once consumed
+            len = blocks;
+        }
+    }
+    void cg_iteration() {   // one pass of the loop body (:797-829); all kernels no-op once sc->done
+        k_pupdate<<<grid1d(np, 256), 256, 0, st>>>(p, r, np, sc);
+        Ab(p, y, done_ptr());
+        Atx_prefix(y, done_ptr());
+        k_atx_combine<1><<<(unsigned)nblk, 256, 0, st>>>(P, PRS, w, n, np, active, p, part1, done_ptr());
+        finish_tree(EP_ALPHA, 1);
+        k_xr_update<<<(unsigned)nblk, 256, 0, st>>>(x, r, p, w, np, sc, part1);
+        finish_tree(EP_RHO_STEP, 1);
+        launches += 3;
+    }
+    // circularConjugateGrads (:769-831) with b = AtWd
+    int conjugate_grads() {
+        ++cg_calls;
+        h_sc->k = 0;
+        FNN_CUDA(cudaMemsetAsync(&sc->done, 0, sizeof(int), st));
+        FNN_CUDA(cudaMemsetAsync(&sc->k, 0, sizeof(long long), st));
+        Ab(x, y, nullptr);
+        Atx(y, r, nullptr);
+        k_residual_init<<<(unsigned)nblk, 256, 0, st>>>(r, AtWd, active, np, part1);
+        finish_tree(EP_RHO_INIT, 0);
+        launches += 1;
+        if (!cg_graph) {
+            cudaGraph_t g;
+            const int64_t before = launches;
+            FNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            for (int i = 0; i < 8; ++i) cg_iteration();
+            FNN_CUDA(cudaStreamEndCapture(st, &g));
+            launches_per_graph = launches - before;
+            launches = before;
+            FNN_CUDA(cudaGraphInstantiate(&cg_graph, g, 0));
+            cudaGraphDestroy(g);
+        }
+        while (true) {
+            FNN_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+            FNN_CUDA(cudaStreamSynchronize(st));
+            if (h_sc->done) break;
+            for (int rep = 0; rep < 4; ++rep) { FNN_CUDA(cudaGraphLaunch(cg_graph, st)); launches += launches_per_graph; }
+        }
+        return FNN_OK;
+    }
+};
+
+template <typename InOp>
+static int minloc_reduce(Csw& c, InOp op, MinLoc* out_host) {
+    static thread_local void* tmp = nullptr;
+    static thread_local size_t tmp_bytes = 0;
+    static thread_local MinLoc* d_out = nullptr;
+    if (!d_out) FNN_CUDA(cudaMalloc((void**)&d_out, sizeof(MinLoc)));
+    cub::CountingInputIterator<long long> cnt(0);
+    cub::TransformInputIterator<MinLoc, InOp, cub::CountingInputIterator<long long>> it(cnt, op);
+    size_t need = 0;
+    FNN_CUDA(cub::DeviceReduce::Reduce(nullptr, need, it, d_out, (int)c.np, MinLocOp(), MinLoc{0.0, -1}, c.st));
+    if (need > tmp_bytes) { if (tmp) cudaFree(tmp); FNN_CUDA(cudaMalloc(&tmp, need)); tmp_bytes = need; }
+    FNN_CUDA(cub::DeviceReduce::Reduce(tmp, need, it, d_out, (int)c.np, MinLocOp(), MinLoc{0.0, -1}, c.st));
+    FNN_CUDA(cudaMemcpyAsync(out_host, d_out, sizeof(MinLoc), cudaMemcpyDeviceToHost, c.st));
+    FNN_CUDA(cudaStreamSynchronize(c.st));
+    return FNN_OK;
+}
+
+// worstIndices(x, 0.6) + contraction (:282-330, :420-431); returns whether anything was contracted
+static int contract_worst(Csw& c, bool* contracted) {
+    static thread_local void* tmp = nullptr;
+    static thread_local size_t tmp_bytes = 0;
+    static thread_local double *neg = nullptr, *neg_sorted = nullptr;
+    static thread_local int *d_count = nullptr, *tie_flag = nullptr, *tie_rank = nullptr;
+    static thread_local int64_t cap = 0;
+    if (cap < c.np) {
+        if (neg) { cudaFree(neg); cudaFree(neg_sorted); cudaFree(tie_flag); cudaFree(tie_rank); cudaFree(d_count); }
+        FNN_CUDA(cudaMalloc((void**)&neg, sizeof(double) * c.np));
+        FNN_CUDA(cudaMalloc((void**)&neg_sorted, sizeof(double) * c.np));
+        FNN_CUDA(cudaMalloc((void**)&tie_flag, sizeof(int) * c.np));
+        FNN_CUDA(cudaMalloc((void**)&tie_rank, sizeof(int) * c.np));
+        FNN_CUDA(cudaMalloc((void**)&d_count, sizeof(int)));
+        cap = c.np;
+    }
+    auto ensure = [&](size_t need) -> int {
+        if (need > tmp_bytes) { if (tmp) cudaFree(tmp); FNN_CUDA(cudaMalloc(&tmp, need)); tmp_bytes = need; }
+        return FNN_OK;
+    };
+    size_t need = 0;
+    FNN_CUDA(cub::DeviceSelect::If(nullptr, need, c.x, neg, d_count, (int)c.np, IsNeg(), c.st));
+    if (ensure(need)) return FNN_E_CUDA;
+    FNN_CUDA(cub::DeviceSelect::If(tmp, need, c.x, neg, d_count, (int)c.np, IsNeg(), c.st));
+    int numNeg = 0;
+    FNN_CUDA(cudaMemcpyAsync(&numNeg, d_count, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+    FNN_CUDA(cudaStreamSynchronize(c.st));
+    *contracted = false;
+    if (numNeg == 0) return FNN_OK;
+    need = 0;
+    FNN_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, neg, neg_sorted, numNeg, 0, 64, c.st));
+    if (ensure(need)) return FNN_E_CUDA;
+    FNN_CUDA(cub::DeviceRadixSort::SortKeys(tmp, need, neg, neg_sorted, numNeg, 0, 64, c.st));
+    const int64_t nkept = (int64_t)std::ceil(0.6 * (double)numNeg);
+    double cutoff = 0.0;
+    FNN_CUDA(cudaMemcpyAsync(&cutoff, neg_sorted + (nkept - 1), sizeof(double), cudaMemcpyDeviceToHost, c.st));
+    // number strictly below the cutoff = first index of cutoff in the sorted negatives (binary search on host copy is
+    // avoided: count with the tie scan below)
+    FNN_CUDA(cudaStreamSynchronize(c.st));
+    k_mark_below<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.active, c.np, cutoff, tie_flag);
+    // strictly-less count: lower_bound in neg_sorted
+    need = 0;
+    FNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, tie_flag, tie_rank, (int)c.np, c.st));
+    if (ensure(need)) return FNN_E_CUDA;
+    FNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, need, tie_flag, tie_rank, (int)c.np, c.st));
+    // ties fill result[back--] while back >= front: slots = nkept - (#strictly less)
+    // #strictly less = numNeg_sorted lower_bound(cutoff): fetch by a tiny device binary search on the host side
+    int64_t lo = 0, hi = nkept - 1;   // neg_sorted[nkept-1] == cutoff, so the lower bound is in [0, nkept-1]
+    if (nkept >= 2) {   // common case: no tie at the cutoff
+        double prev;
+        FNN_CUDA(cudaMemcpyAsync(&prev, neg_sorted + (nkept - 2), sizeof(double), cudaMemcpyDeviceToHost, c.st));
+        FNN_CUDA(cudaStreamSynchronize(c.st));
+        if (prev < cutoff) lo = hi;
+    }
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) / 2;
+        double v;
+        FNN_CUDA(cudaMemcpyAsync(&v, neg_sorted + mid, sizeof(double), cudaMemcpyDeviceToHost, c.st));
+        FNN_CUDA(cudaStreamSynchronize(c.st));
+        if (v < cutoff) lo = mid + 1; else hi = mid;
+    }
+    const int64_t slots = nkept - lo;
+    k_mark_ties<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.active, c.np, tie_flag, tie_rank, slots);
+    c.launches += 6;
+    *contracted = true;
+    return FNN_OK;
+}
+
+// runActiveConjugate (:359-557)
+static int active_conjugate(Csw& c) {
+    const int n = c.n;
+    k_unconstrained<<<c.grid_rows(), 256, 0, c.st>>>(c.d, c.x, n);
+    MinLoc ml;
+    {   // all_positive test (:369-374): any x < 0 ?
+        if (minloc_reduce(c, RatioIn{c.x, c.x}, &ml)) return FNN_E_CUDA;   // only the index matters here
+        if (ml.i < 0) return FNN_OK;
+    }
+    k_fill<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.old_x, c.np, 1.0);
+    FNN_CUDA(cudaMemsetAsync(c.active, 0, c.np, c.st));
+    c.Atx(c.d, c.AtWd, nullptr);   // y = W*d = d
+    // e_0 depends only on b = AtWd: compute once
+    k_square_partials<<<(unsigned)c.nblk, 256, 0, c.st>>>(c.AtWd, c.np, c.part1);
+    c.finish_tree(EP_E0, 0);
+    FNN_CUDA(cudaMemcpyAsync(&c.sc->kmax, &c.np, sizeof(long long), cudaMemcpyHostToDevice, c.st));
+    bool first_pass = true;
+    while (true) {
+        ++c.outer;
+        while (true) {
+            ++c.inner;
+            if (!first_pass) { if (c.conjugate_grads()) return FNN_E_CUDA; }
+            first_pass = false;
+            bool contracted = false;
+            if (contract_worst(c, &contracted)) return FNN_E_CUDA;
+            if (contracted) { if (c.conjugate_grads()) return FNN_E_CUDA; }
+            if (minloc_reduce(c, RatioIn{c.x, c.old_x}, &ml)) return FNN_E_CUDA;
+            if (ml.i < 0) break;
+            k_oldx_step<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.old_x, c.x, c.active, c.np, ml.v);
+            k_set_one<<<1, 32, 0, c.st>>>(c.x, c.active, ml.i, 0.0, 1, 1);
+            c.launches += 2;
+        }
+        c.Ab(c.x, c.y, nullptr);
+        c.Atx(c.y, c.r, nullptr);
+        k_gradient<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.r, c.AtWd, c.np);
+        if (minloc_reduce(c, GradIn{c.r, c.active}, &ml)) return FNN_E_CUDA;
+        if (ml.i < 0 || ml.v > -0.0000001) return FNN_OK;
+        k_set_one<<<1, 32, 0, c.st>>>(c.x, c.active, ml.i, 0.0, 0, 0);
+    }
+}
+
+}  // namespace
+
+extern "C" int fnn_csw_matvec(const fnn_opts* o, int32_t which, const double* v, int64_t n, double* out) {
+    if (!v || !out || n < 4 || n > 30000) { fnn::set_error("fnn_csw_matvec: bad arguments"); return FNN_E_ARG; }
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) { cudaGetLastError(); fnn::set_error("no CUDA device available (libfastnn has no CPU fallback)"); return FNN_E_NODEVICE; }
+    FNN_CUDA(cudaSetDevice(o ? o->device : 0));
+    Csw c;
+    c.n = (int)n; c.np = n * (n - 1) / 2; c.nblk = (c.np + 1023) / 1024;
+    int rc = c.alloc();
+    if (!rc) {
+        cudaMemcpyAsync(c.x, v, sizeof(double) * c.np, cudaMemcpyHostToDevice, c.st);
+        if (which == 0) c.Ab(c.x, c.y, nullptr);
+        else if (which == 1) c.Atx(c.x, c.y, nullptr);
+        else k_unconstrained<<<c.grid_rows(), 256, 0, c.st>>>(c.x, c.y, c.n);
+        cudaMemcpyAsync(out, c.y, sizeof(double) * c.np, cudaMemcpyDeviceToHost, c.st);
+        if (cudaStreamSynchronize(c.st) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            fnn::set_error("fnn_csw_matvec: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = FNN_E_CUDA;
+        }
+    }
+    c.release();
+    return rc;
+}
+
+extern "C" int fnn_split_weights(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double* x_out,
+                                 int64_t* stats_out) {
+    if (!ordering || !d_upper || !x_out || n < 4 || n > 30000) { fnn::set_error("fnn_split_weights: bad arguments (4 <= n <= 30000)"); return FNN_E_ARG; }
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) { cudaGetLastError(); fnn::set_error("no CUDA device available (libfastnn has no CPU fallback)"); return FNN_E_NODEVICE; }
+    FNN_CUDA(cudaSetDevice(o ? o->device : 0));
+    Csw c;
+    c.n = (int)n; c.np = n * (n - 1) / 2; c.nblk = (c.np + 1023) / 1024;
+    int rc = c.alloc();
+    int* d_ord = nullptr;
+    if (!rc) {
+        FNN_CUDA(cudaMalloc((void**)&d_ord, sizeof(int) * (n + 1)));
+        FNN_CUDA(cudaMemcpyAsync(d_ord, ordering, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c.st));
+        FNN_CUDA(cudaMemcpyAsync(c.r, d_upper, sizeof(double) * c.np, cudaMemcpyHostToDevice, c.st));   // r as staging
+        k_setup_d<<<c.grid_rows(), 256, 0, c.st>>>(c.r, d_ord, c.d, c.n);
+        const bool unconstrained = o && o->reserved[3] == 1;
+        if (unconstrained) k_unconstrained<<<c.grid_rows(), 256, 0, c.st>>>(c.d, c.x, c.n);
+        else rc = active_conjugate(c);
+        if (!rc) {
+            FNN_CUDA(cudaMemcpyAsync(x_out, c.x, sizeof(double) * c.np, cudaMemcpyDeviceToHost, c.st));
+            FNN_CUDA(cudaMemcpyAsync(c.h_sc, c.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c.st));
+            FNN_CUDA(cudaStreamSynchronize(c.st));
+            FNN_CUDA(cudaGetLastError());
+            if (stats_out) { stats_out[0] = c.h_sc->iters_total; stats_out[1] = c.cg_calls; stats_out[2] = c.outer; stats_out[3] = c.inner; stats_out[4] = c.launches; }
+        }
+    }
+    if (d_ord) cudaFree(d_ord);
+    c.release();
+    return rc;
+}

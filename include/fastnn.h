@@ -106,6 +106,22 @@ int fnn_order(const fnn_opts* o, const double* D_rowmajor, const char* phylip_pa
 /* initial cluster row sums only (NetMakerOriginal.initialize, :164-191) — kernel K1, exposed for parity tests */
 int fnn_rowsums(const fnn_opts* o, const double* D_rowmajor, int64_t n, double* Sx_out);
 
+/* B2: replaces the split-weight stage of FastNN.main (FastNN.java:401-466 live dense NNLS; intended call
+ * FastNN.java:509-511 -> CircularSplitWeights.getWeightedSplits/getWeights, CircularSplitWeights.java:67,162)
+ * with var="ols", constrained=true.  ordering: the n+1 ints of fnn_order; d_upper: the npairs = n(n-1)/2 packed
+ * upper triangle in FILE order (DistancesAndNames.get(), DistancesAndNames.java:24-38,138).  x_out[npairs] uses the
+ * LIVE indexing of FastNN.java:409-418: entry (i,j), i<j, row-major upper, is the split {ordering[i+1..j]}, so the
+ * `x > 1e-6` filter of FastNN.java:455-466 and OutputPrinter work unchanged.  opts.reserved[3] = 1 returns the
+ * unconstrained closed form only (the `useMax && maxIterations == 1` branch, CircularSplitWeights.java:166-167).
+ * stats_out (optional, 5 entries): CG iterations, CG calls, outer passes, inner passes, kernel launches. */
+int fnn_split_weights(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double* x_out,
+                      int64_t* stats_out);
+
+/* single mat-vec / stencil of the split-weight solver on a packed npairs vector, for kernel parity tests:
+ * which = 0: d = A b (calculateAb, CircularSplitWeights.java:643-731); 1: p = A^T d (calculateAtx, :603-633);
+ * 2: unconstrained closed form (runUnconstrainedLS, :247-271) */
+int fnn_csw_matvec(const fnn_opts* o, int32_t which, const double* v, int64_t n, double* out);
+
 /* left-to-right fp64 sums of nrows (<=4) rows of length len, bit-identical to `for (i) s += x[i]`
  * (the accumulation order of ComputeRx / updateClusterDistances, NetMakerOriginal.java:549-561, :530-535),
  * computed by the parallel exact-summation kernel (csrc/fnn_exact_sum.cuh) - exposed for parity tests */

@@ -24,8 +24,8 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "liboracle.so")
-        src = os.path.join(_HERE, "nnet_oracle.cpp")
-        if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+        srcs = [os.path.join(_HERE, f) for f in ("nnet_oracle.cpp", "csw_l1.cpp")]
+        if not os.path.exists(so) or any(os.path.exists(s_) and os.path.getmtime(s_) > os.path.getmtime(so) for s_ in srcs):
             build()
         L = ctypes.CDLL(so)
         c_dp = ctypes.POINTER(ctypes.c_double)
@@ -40,6 +40,11 @@ def lib():
         L.oracle_atx.argtypes = [ctypes.c_int64, c_dp, c_dp]
         L.oracle_ab.argtypes = [ctypes.c_int64, c_dp, c_dp]
         L.oracle_split_weights.argtypes = [ctypes.c_int64, c_dp, c_dp, ctypes.c_int, c_lp]
+        L.oracle_l1_ab.argtypes = [ctypes.c_int64, c_dp, c_dp]
+        L.oracle_l1_atx.argtypes = [ctypes.c_int64, c_dp, c_dp]
+        L.oracle_l1_tree_sum.argtypes = [c_dp, ctypes.c_int64]
+        L.oracle_l1_tree_sum.restype = ctypes.c_double
+        L.oracle_l1_split_weights.argtypes = [ctypes.c_int64, c_dp, c_dp, c_lp]
         L.oracle_java_random.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_ip]
         _LIB = L
     return _LIB
@@ -123,3 +128,20 @@ def java_random(seed, bound, count):
     out = np.zeros(count, dtype=np.int32)
     lib().oracle_java_random(seed, bound, count, _ip(out))
     return out
+
+
+def l1_ab(n, b):
+    return _vec(lib().oracle_l1_ab, n, b)
+
+
+def l1_atx(n, d):
+    return _vec(lib().oracle_l1_atx, n, d)
+
+
+def l1_split_weights(n, d_pos):
+    """Parity-ladder level L1: the GPU's formulation and reduction trees restated on the CPU (csw_l1.cpp)."""
+    d = np.ascontiguousarray(d_pos, dtype=np.float64)
+    x = np.zeros_like(d)
+    st = np.zeros(4, dtype=np.int64)
+    lib().oracle_l1_split_weights(n, _dp(d), _dp(x), _lp(st))
+    return x, {"cg_iters": int(st[0]), "cg_calls": int(st[1]), "outer": int(st[2]), "inner": int(st[3])}

@@ -126,3 +126,40 @@ def test_phylip_roundtrip(tmp_path):
     synth.write_phylip(str(p), D)
     D2, names = synth.read_phylip(str(p))
     assert (D2 == D).all() and names[0] == "t1"
+
+
+# ---- split weights: the parity ladder on the CPU (L0 literal, L1 GPU-order restatement, dense NNLS) ----
+def _csw_problem(n, seed, eps=0.05):
+    D = tree_matrix(n, seed, eps)
+    o, _, _ = oracle.order(D)
+    du = synth.upper_triangle(D)
+    return D, o, du, oracle.setup_d(o, du)
+
+
+def test_csw_matvec_formulations_agree():
+    rng = np.random.default_rng(1)
+    for n in (4, 5, 9, 33, 70):
+        v = rng.random(n * (n - 1) // 2)
+        assert np.abs(oracle.l1_ab(n, v) - oracle.ab(n, v)).max() <= 1e-13 * v.sum()
+        assert np.abs(oracle.l1_atx(n, v) - oracle.atx(n, v)).max() <= 1e-13 * v.sum()
+
+
+def test_csw_l0_l1_and_dense_nnls():
+    from scipy.optimize import nnls
+    for n, seed in ((8, 1), (12, 2), (16, 3)):
+        D, o, du, d_pos = _csw_problem(n, seed)
+        x0, s0 = oracle.split_weights(n, d_pos)
+        x1, s1 = oracle.l1_split_weights(n, d_pos)
+        A = np.array(pyref.live_design_matrix(n, o.tolist()))
+        xs, _ = nnls(A, du, maxiter=100000)
+        # rotated permutation: CSW indexing == live indexing, same support, ~1e-5 agreement
+        assert np.abs(x0 - xs).max() < 1e-4 and np.abs(x1 - xs).max() < 1e-4
+        assert (x0 >= 0).all() and (x1 >= 0).all()
+
+
+def test_csw_additive_tree_reproduces_distances():
+    """eps = 0: circular split weights of a tree metric reproduce the metric: A x = d."""
+    n = 20
+    D, o, du, d_pos = _csw_problem(n, 7, 0.0)
+    x, _ = oracle.split_weights(n, d_pos)
+    assert np.abs(oracle.ab(n, x) - d_pos).max() < 1e-9
