@@ -64,6 +64,10 @@ struct DevState {
     int chg_src[MAXK];
     double chg_Sx[MAXK];
     int final3[4];
+    // mode-specific selection (Relaxed: written by the host; Random: by k_random_select)
+    int mode, mult, fallback, cx_pos, cy_pos;
+    int pick_x_id, pick_y_id, pick_kind;
+    unsigned long long rng;       // java.util.Random state (48 bits)
     double Dmax;                  // max |D| at load time (slack of the scan's filter, fnn_scan_tma.cuh)
     double alg_bytes;             // running sum of the selection scan's algorithmic bytes
 };
@@ -81,14 +85,17 @@ __device__ __forceinline__ bool better(double q, unsigned long long k, double bq
 namespace {
 #include "fnn_scan_tma.cuh"
 #include "fnn_exact_sum.cuh"
+#include "fnn_modes.cuh"
 
 // ------------------------------------------------------------------ init kernels
-__global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st) {
+__global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st, int mode, int mult, int fallback, long long seed) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) { id[t] = t + 1; pos[t] = t; p2s[t] = t; }
     if (t == 0) {
         memset(st, 0, sizeof(DevState));
         st->m = n; st->c = n; st->P2 = 0; st->num_nodes = n;
+        st->mode = mode; st->mult = mult; st->fallback = fallback;
+        st->rng = ((unsigned long long)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);   // java.util.Random(seed)
     }
 }
 
@@ -128,7 +135,7 @@ template <int TR>
 __global__ void __launch_bounds__(SCAN_THREADS, 2)
 k_scan(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ pos,
        DevState* st, Partial* partials) {
-    if (st->done) return;
+    if (st->done || (st->mode != 0 && st->m > st->fallback)) return;   // NetMakerOriginal.java:361-366
     const int m = st->m, P2 = st->P2;
     const double cm2 = (double)st->c - 2.0;
     constexpr int KPB = TILE_W / TR;  // row tiles per 512-row band
@@ -431,10 +438,13 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
 
     // ---- Cx, Cy from the scan key; id-order swap (:376-380)
     if (tid == 0) {
-        int cx = p2s[st->sel_i], cy = p2s[st->sel_j];
+        int cx, cy;
+        if (st->mode != 0 && m > st->fallback) { cx = p2s[st->cx_pos]; cy = p2s[st->cy_pos]; }   // Relaxed / Random findNodes
+        else { cx = p2s[st->sel_i]; cy = p2s[st->sel_j]; }
         if (id[cx] > id[cy]) { int t = cx; cx = cy; cy = t; }
         sh[0] = cx; sh[1] = nbr_of(cx, P2); sh[2] = cy; sh[3] = nbr_of(cy, P2);
-        st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
+        if (st->mode == 0 || m <= st->fallback)
+            st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
     }
     __syncthreads();
     const int Cx = sh[0], Cxn = sh[1], Cy = sh[2], Cyn = sh[3];
@@ -475,6 +485,7 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
     }
     const int xn = nbr_of(x, P2), yn = nbr_of(y, P2);
     st->sx = x; st->sxn = xn; st->sy = y; st->syn = yn;
+    st->pick_x_id = id[x]; st->pick_y_id = id[y];
     const int nn = st->num_nodes;
     int K = 0;
     int cslot[MAXK], csrc[MAXK], cid[MAXK], cpos[MAXK];
@@ -547,6 +558,7 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
     }
     if (trace) trace[8 * (int64_t)st->iter + 6] = kind;
     st->kind = kind;
+    st->pick_kind = kind;
     st->K = K;
     // publish the new layout's node tables (sources were captured above, so overlaps are safe)
     for (int k = 0; k < K; ++k) {
@@ -803,8 +815,9 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     fnn_opts d;
     if (!o) { fnn_default_opts(&d); o = &d; }
     if (n > 2000000) { fnn::set_error("n too large"); return FNN_E_ARG; }
-    if (o->mode != FNN_CANONICAL && n > o->canonical_fallback) {
-        fnn::set_error("mode %d is not implemented on the device yet (canonical only)", o->mode);
+    if (o->mode < 0 || o->mode > FNN_RANDOM_LOGN) { fnn::set_error("unknown mode %d", o->mode); return FNN_E_ARG; }
+    if (o->mode == FNN_RELAXED && o->additive && n > o->canonical_fallback) {
+        fnn::set_error("-additive look-ahead (NeighborNetLocal.java:223-255) is not implemented on the device yet");
         return FNN_E_UNSUPPORTED;
     }
     int rc = ensure_device(o);
@@ -936,11 +949,159 @@ static int make_tensor_map(fnn_ctx* c) {
     return FNN_OK;
 }
 static inline void launch_rest(fnn_ctx* c) {
+    if (c->o.mode >= FNN_RANDOM_N)
+        modes::k_random_select<<<1, modes::THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->p2s, c->st);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
                                                     c->o.reserved[1] != 2);
     k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
     k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage);
     k_chain<<<1, PICK_THREADS, CHAIN_SMEM, c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage, c->o.reserved[1] != 2);
+}
+
+
+// ---------------------------------------------------------------- Relaxed: host control flow
+// The sampling / mutual-nearest logic of NeighborNetLocal.findNodes (NeighborNetLocal.java:170-264) is
+// branchy control flow over a handful of row scans per iteration; it runs here on the host against a
+// mirror of the reference's node table, calling k_rowmin for every findRowMin (:88-157).
+namespace {
+struct JavaRandomHost {   // java.util.Random(seed), same stream as the device generator
+    uint64_t s;
+    explicit JavaRandomHost(int64_t seed) { s = ((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1); }
+    int32_t next(int bits) { s = (s * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1); return (int32_t)((int64_t)s >> (48 - bits)); }
+    int32_t nextInt(int32_t bound) {
+        int32_t r = next(31);
+        const int32_t m = bound - 1;
+        if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+        for (int32_t u = r;; u = next(31)) {
+            r = u % bound;
+            if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) break;
+        }
+        return r;
+    }
+};
+
+struct Mirror {   // ids, neighbours and positions only; distances and row sums stay on the device
+    std::vector<int> pos, nbr;   // by node id (1-based); nbr 0 = none
+    std::vector<int> act;        // netNodes[]: node id per position
+    int m = 0, c = 0, nn = 0;
+    void init(int n) {
+        pos.assign(3 * n + 8, -1); nbr.assign(3 * n + 8, 0); act.assign(n, 0);
+        for (int i = 1; i <= n; ++i) { pos[i] = i - 1; act[i - 1] = i; }
+        m = c = nn = n;
+    }
+    int agg3(int x, int y, int z, int num_active) {   // position bookkeeping of agg3way (NetMakerOriginal.java:608-648)
+        const int u = nn + 1, v = nn + 2;
+        nn += 2;
+        act[pos[x]] = u; pos[u] = pos[x];
+        act[pos[z]] = v; pos[v] = pos[z];
+        const int last = act[num_active - 1];
+        act[pos[y]] = last; pos[last] = pos[y];
+        act[num_active - 1] = 0;
+        nbr[u] = v; nbr[v] = u;
+        return u;
+    }
+    void apply(int x, int y) {   // handleAgglomerationEvent's dispatch (:462-488)
+        if (nbr[x] == 0 && nbr[y] == 0) { nbr[x] = y; nbr[y] = x; }
+        else if (nbr[x] == 0) { agg3(x, y, nbr[y], m); m -= 1; }
+        else if (nbr[y] == 0 || m == 4) { agg3(y, x, nbr[x], m); m -= 1; }
+        else {
+            const int x2 = nbr[x], y2 = nbr[y];
+            const int u = agg3(x2, x, y, m);
+            agg3(u, nbr[u], y2, m - 1);
+            m -= 2;
+        }
+        c -= 1;
+    }
+};
+
+struct RowMinHost { int me, row; double value; };
+}  // namespace
+
+static int run_relaxed(fnn_ctx* c, int64_t& launches) {
+    const int n = (int)c->n;
+    Mirror mir;
+    mir.init(n);
+    JavaRandomHost rng((int64_t)c->o.seed);
+    std::vector<int> rowPerm(n);
+    for (int i = 0; i < n; ++i) rowPerm[i] = i;
+    int top = n - 1;
+    modes::RowMinOut* d_out = nullptr;
+    modes::RowMinOut* h_out = nullptr;
+    FNN_CUDA(cudaMalloc((void**)&d_out, sizeof(modes::RowMinOut)));
+    FNN_CUDA(cudaMallocHost((void**)&h_out, sizeof(modes::RowMinOut)));
+    int rc = FNN_OK;
+    int Cx = 0, Cy = 0;   // node ids; persist across iterations like the Java fields
+    std::vector<std::vector<RowMinHost>> lists;
+    while (mir.m > c->o.canonical_fallback && mir.m > 3) {
+        std::vector<std::pair<int, int>> found;   // node id -> list index (HashMap with identity keys)
+        lists.clear();
+        auto lookup = [&](int node) -> int { for (auto& kv : found) if (kv.first == node) return kv.second; return -1; };
+        auto findRowMin = [&](int p) -> int {
+            int li = lookup(p);
+            if (li >= 0) return li;
+            if (mir.nbr[p]) { li = lookup(mir.nbr[p]); if (li >= 0) return li; }
+            modes::k_rowmin<<<1, modes::THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, mir.pos[p], d_out);
+            ++launches;
+            if (cudaMemcpyAsync(h_out, d_out, 16, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess) return -2;
+            if (h_out->overflow) return -3;
+            if (h_out->count > 0 &&
+                (cudaMemcpyAsync(h_out->pos, d_out->pos, sizeof(int) * h_out->count, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                 cudaStreamSynchronize(c->stream) != cudaSuccess)) return -2;
+            std::vector<RowMinHost> l;
+            for (int k = 0; k < h_out->count; ++k) l.push_back({p, mir.act[h_out->pos[k]], h_out->value});
+            lists.push_back(std::move(l));
+            found.push_back({p, (int)lists.size() - 1});
+            return (int)lists.size() - 1;
+        };
+        std::vector<RowMinHost> myMinimums;
+        bool chosen = false;
+        for (int i = top + 1; i > 0 && !chosen; i--) {   // :185-260
+            const int swapCell = rng.nextInt(i);
+            if (rowPerm[swapCell] >= mir.m) {
+                std::swap(rowPerm[swapCell], rowPerm[top]);
+                if (i == top + 1) i--; else i++;
+                top--;
+                continue;
+            }
+            std::swap(rowPerm[i - 1], rowPerm[swapCell]);
+            const int p = mir.act[rowPerm[i - 1]];
+            if (mir.nbr[p] && mir.nbr[p] < p) continue;
+            const int li = findRowMin(p);
+            if (li < 0) { rc = li == -3 ? FNN_E_UNSUPPORTED : FNN_E_CUDA; break; }
+            for (size_t a = 0; a < lists[li].size(); ++a) {
+                const RowMinHost myRM = lists[li][a];
+                const int lo = findRowMin(myRM.row);
+                if (lo < 0) { rc = lo == -3 ? FNN_E_UNSUPPORTED : FNN_E_CUDA; break; }
+                for (size_t b = 0; b < lists[lo].size(); ++b) {
+                    const RowMinHost t = lists[lo][b];
+                    const int rn = mir.nbr[t.row], pn = mir.nbr[p];
+                    if (t.row == p || (rn && rn == p) || (rn && pn && rn == pn) || (pn && t.row == pn)) { myMinimums.push_back(t); break; }
+                }
+            }
+            if (rc) break;
+            if (!myMinimums.empty()) {
+                const RowMinHost pick = myMinimums[rng.nextInt((int)myMinimums.size())];
+                Cx = pick.me; Cy = pick.row;
+                chosen = true;   // non-additive: break outerloop (:257)
+            }
+        }
+        if (rc) break;
+        if (Cx == 0 || Cy == 0) { fnn::set_error("relaxed selection found no pair"); rc = FNN_E_STATE; break; }
+        // hand (Cx, Cy) to the device as positions, run the agglomeration event, read back the chosen nodes
+        int sel[2] = {mir.pos[Cx], mir.pos[Cy]};
+        FNN_CUDA(cudaMemcpyAsync(&c->st->cx_pos, sel, sizeof(sel), cudaMemcpyHostToDevice, c->stream));
+        launch_rest(c);
+        launches += 4;
+        FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+        FNN_CUDA(cudaStreamSynchronize(c->stream));
+        mir.apply(c->h_st->pick_x_id, c->h_st->pick_y_id);
+        if (mir.m != c->h_st->m) { fnn::set_error("host mirror out of sync (m=%d vs %d)", mir.m, c->h_st->m); rc = FNN_E_STATE; break; }
+    }
+    if (rc == FNN_E_UNSUPPORTED) fnn::set_error("relaxed row scan: more than %d exact ties in one row", modes::MAX_TIES);
+    cudaFree(d_out);
+    cudaFreeHost(h_out);
+    return rc;
 }
 
 // expandNodes (NetMakerOriginal.java:246-325) on the host from the amalgamation log
@@ -985,7 +1146,8 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     FNN_CUDA(cudaEventCreate(&e0)); FNN_CUDA(cudaEventCreate(&e1));
     FNN_CUDA(cudaEventRecord(e0, c->stream));
     const int ni = (int)n;
-    k_init_nodes<<<(ni + 255) / 256, 256, 0, c->stream>>>(ni, c->id, c->pos, c->p2s, c->st);
+    k_init_nodes<<<(ni + 255) / 256, 256, 0, c->stream>>>(ni, c->id, c->pos, c->p2s, c->st, c->o.mode, c->o.mult,
+                                                          c->o.canonical_fallback, (long long)c->o.seed);
     k_rowsum<<<(ni + 127) / 128, 128, 0, c->stream>>>(c->D, c->ld, ni, c->Sx, c->st);
     FNN_CUDA(cudaGetLastError());
     int64_t launches = 2, scans = 0;
@@ -993,6 +1155,10 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     double prof_ms = 0.0, prof_bytes = 0.0;
     int64_t prof_samples = 0;
 
+    if (c->o.mode == FNN_RELAXED && n > c->o.canonical_fallback) {
+        int rrc = run_relaxed(c, launches);   // until num_active <= canonical_fallback; the tail below is canonical
+        if (rrc) return rrc;
+    }
     if (c->o.profile_every > 0) {
         // sampled per-launch timing of the selection kernel (roofline.achieved in bench.py)
         cudaEvent_t p0, p1;
@@ -1037,7 +1203,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
             const int64_t batch = 64;  // graphs between done-flag polls
             for (int64_t b = 0; b < batch && it < max_iters; ++b, it += GI) {
                 FNN_CUDA(cudaGraphLaunch(c->graph, c->stream));
-                launches += 5 * GI; scans += GI;
+                launches += (5 + (c->o.mode >= FNN_RANDOM_N)) * GI; scans += GI;
             }
             FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
             FNN_CUDA(cudaStreamSynchronize(c->stream));

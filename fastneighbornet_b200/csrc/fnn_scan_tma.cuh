@@ -197,7 +197,7 @@ __device__ __forceinline__ void eval_pp(const double* sm, const RowData* rd, dou
 __global__ void __launch_bounds__(THREADS, 1)
 k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ Sx, const int* __restrict__ pos,
            DevState* st, Partial* partials) {
-    if (st->done) return;
+    if (st->done || (st->mode != 0 && st->m > st->fallback)) return;   // NetMakerOriginal.java:361-366
     extern __shared__ __align__(1024) unsigned char smem[];
     // keep the ring pointer in the shared window (no generic-address loads): offset, not integer cast
     double* ring = reinterpret_cast<double*>(smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u));

@@ -1,0 +1,57 @@
+"""Relaxed and Random selection on the device against the oracle under the same java.util.Random seed
+(the reference's ThreadLocalRandom is unseedable; DESIGN.md "RNG contract"): ordering and the whole
+per-iteration trace must be identical."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import integer_matrix, random_matrix, tree_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(fnn, D, mode, seed, fallback, mult=5):
+    with fnn.Context(D.shape[0], record_trace=1, mode=mode, seed=seed, canonical_fallback=fallback, mult=mult) as c:
+        c.load_host(D)
+        o = c.order()
+        return o, c.trace()
+
+
+def _check(fnn, D, mode, seed=777, fallback=8, mult=5):
+    o_ref, tr_ref, _ = oracle.order(D, mode=mode, seed=seed, fallback=fallback, mult=mult)
+    o, tr = _run(fnn, D, mode, seed, fallback, mult)
+    assert tr.shape == tr_ref.shape
+    bad = np.nonzero((tr != tr_ref).any(axis=1))[0]
+    assert bad.size == 0, f"{mode}: first diverging iteration {bad[0]}: gpu={tr[bad[0]]} ref={tr_ref[bad[0]]}"
+    assert (o == o_ref).all()
+
+
+@pytest.mark.parametrize("mode", ["relaxed", "random_n", "random_nlogn", "random_logn"])
+@pytest.mark.parametrize("n", [12, 33, 100, 300])
+def test_modes_small_with_low_fallback(fnn, mode, n):
+    for seed in (1, 2):
+        for D in (tree_matrix(n, seed, 0.0), tree_matrix(n, seed, 0.1), random_matrix(n, seed)):
+            _check(fnn, D, mode, seed=100 + seed)
+
+
+@pytest.mark.parametrize("mode", ["relaxed", "random_n"])
+def test_modes_with_ties(fnn, mode):
+    _check(fnn, integer_matrix(120, 3), mode, seed=5)
+
+
+@pytest.mark.parametrize("mode", ["relaxed", "random_logn", "random_n"])
+def test_modes_default_fallback_n1500(fnn, mode):
+    """Default canonical_fallback = 1024 (NetMakerOriginal.java:361): the strategy runs for m > 1024, the tail is canonical."""
+    _check(fnn, tree_matrix(1500, 4, 0.05), mode, seed=12345, fallback=1024)
+
+
+def test_random_mult(fnn):
+    _check(fnn, tree_matrix(200, 2, 0.05), "random_nlogn", seed=9, mult=2)
+
+
+def test_reference_style_classes_modes(fnn):
+    D = tree_matrix(1200, 11)
+    o_ref, _, _ = oracle.order(D, mode="relaxed", seed=12345)
+    assert (fnn.NeighborNetLocal(D, 1200, 1, False, None).runNeighborNet() == o_ref).all()
+    o_ref, _, _ = oracle.order(D, mode="random_logn", seed=12345, mult=3)
+    assert (fnn.NeighborNetRandom(D, 1200, 1, None, "LOGN", 3).runNeighborNet() == o_ref).all()
