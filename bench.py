@@ -16,8 +16,9 @@ between the GPU and the CPU arms; `ms_per_step` is the ordering's wall time.
   cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/, "port": the JAR
             cannot run here - no JVM) on a bounded sample (smaller n), all host threads.
 
-N>1: one process per GPU.  Round 1 runs REPLICAS (each rank orders its own matrix; row-sharding
-of one matrix with an NVLink min-loc exchange is the next step), so scaling is "weak".
+N>1: one process per GPU, ONE job: the selection scan (the Theta(n^3) part) is sharded across the
+ranks, the per-rank (Q,i,j) partial min-locs are exchanged through peer-mapped mailboxes over NVLink
+inside the kernels, the Theta(n^2) update is replicated -> scaling is "strong".
 """
 import argparse
 import json
@@ -130,7 +131,7 @@ def run_reference(args, rank, world):
     sample = f"canonical ordering, n={n} (same generator, eps=0.05), {threads} threads, NeighborNetCanonical thread partition"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, world),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -145,7 +146,7 @@ def workload_config(args, world):
         "workload": f"canonical Neighbor-Net ordering (-mode Canonical -order), n={args.n} taxa, synthetic additive tree + 5% noise "
                     f"(BASELINE metric 'n=20k'; fits one GPU: {args.n * args.n * 8 / 1e9:.1f} GB fp64 matrix)",
         "n_taxa": args.n, "mode": "canonical", "eps": 0.05,
-        "parallelism": "single GPU" if world == 1 else f"{world} replicas (one matrix per GPU, no data-path collective)",
+        "parallelism": "single GPU" if world == 1 else f"{world} GPUs: scan sharded by tile, P2P min-loc mailbox exchange, replicated update",
         "l2": f"input matrix {args.n * args.n * 8 / 1e6:.0f} MB >> 126 MB L2; no explicit flush",
     }
 
@@ -188,8 +189,10 @@ def main():
         torch.cuda.synchronize()
 
     n = args.n
-    seed = 1 + rank
+    seed = 1   # every rank holds the same matrix (one job)
     ctx = fnn.Context(n, device=local_rank, use_graph=1)
+    if world > 1:
+        ctx.connect_torch()
     # pristine device copy of the input (torch owns it: plumbing, not the product)
     ctx.synth(seed, 0.05)
     dptr, ld = ctx.matrix_ptr()
@@ -230,9 +233,9 @@ def main():
         t = torch.tensor([elapsed, dev_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed, dev_ms = float(t[0]), float(t[1])
-        b = torch.tensor([alg_bytes, float(launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        b = torch.tensor([float(launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        alg_bytes, launches = float(b[0]), int(b[1])
+        launches = int(b[0])   # alg_bytes is the ONE job's (identical on every rank)
     value = alg_bytes / elapsed / 1e9
 
     # ---- e2e: one-shot C-ABI call with a pinned HOST matrix
@@ -242,23 +245,31 @@ def main():
         host.copy_(pristine[:, :n])  # the ctx matrix itself was consumed by the runs above
         torch.cuda.synchronize()
         Dh = host.numpy()
-        ctx.close()
-        fnn.order(Dh, device=local_rank)  # warm-up (allocator, graph instantiation)
+
+        def e2e_step():
+            if world == 1:
+                return fnn.order(Dh, device=local_rank)   # the one-shot reference-facing seam (fnn_order)
+            ctx.load_host(Dh)                             # N>1: same public API on the wired context
+            return ctx.order()
+
+        if world == 1:
+            ctx.close()
+        e2e_step()  # warm-up (allocator, graph instantiation)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            oe = fnn.order(Dh, device=local_rank)
+            oe = e2e_step()
         barrier()
         e2e_elapsed = time.perf_counter() - t0
         assert (oe == ordering0).all(), "e2e ordering differs from the device-resident run"
-        per_rank_bytes = alg_bytes / world
         if world > 1:
             t = torch.tensor([e2e_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_elapsed = float(t[0])
-        e2e = {"value": per_rank_bytes * world / e2e_elapsed / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * n * 8 * world,
+        e2e = {"value": alg_bytes / e2e_elapsed / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * n * 8 * world,
                "d2h_bytes_per_step": (n + 1) * 4 * world, "ms_per_step": 1e3 * e2e_elapsed / args.steps}
-        ctx = fnn.Context(n, device=local_rank, use_graph=1)
+        if world == 1:
+            ctx = fnn.Context(n, device=local_rank, use_graph=1)
 
     # ---- roofline of the dominant kernel (k_scan), rank 0 only
     roofline, cpu_baseline = None, None
@@ -294,7 +305,7 @@ def main():
         return
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "device_ms_per_step": dev_ms / args.steps, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "fnn_default_opts", "fnn_last_error", "fnn_device_count", "fnn_ctx_create", "fnn_ctx_destroy",
     "fnn_ctx_load_host", "fnn_ctx_load_device", "fnn_ctx_synth", "fnn_ctx_read_matrix", "fnn_ctx_order",
     "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums", "fnn_seq_sum",
-    "fnn_split_weights", "fnn_csw_matvec",
+    "fnn_split_weights", "fnn_csw_matvec", "fnn_ctx_ipc_handle", "fnn_ctx_connect",
 ]
 
 
@@ -92,6 +92,8 @@ def lib():
         L.fnn_ctx_trace.restype = ctypes.c_int64
         L.fnn_ctx_stats.argtypes = [vp, ctypes.POINTER(fnn_stats)]
         L.fnn_ctx_matrix_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]
+        L.fnn_ctx_ipc_handle.argtypes = [vp, ctypes.c_char_p]
+        L.fnn_ctx_connect.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p]
         L.fnn_order.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
         L.fnn_rowsums.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int64, c_dp]
         L.fnn_split_weights.argtypes = [ctypes.POINTER(fnn_opts), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64, c_dp,
@@ -179,6 +181,25 @@ class Context:
         p, ld = ctypes.c_void_p(), ctypes.c_int64()
         _check(lib().fnn_ctx_matrix_ptr(self._h, ctypes.byref(p), ctypes.byref(ld)))
         return p.value, ld.value
+
+    def ipc_handle(self):
+        buf = ctypes.create_string_buffer(64)
+        _check(lib().fnn_ctx_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, rank, world, handles):
+        """handles: list of the `world` 64-byte IPC handles in rank order (e.g. from all_gather_object)."""
+        assert len(handles) == world and all(len(h) == 64 for h in handles)
+        _check(lib().fnn_ctx_connect(self._h, int(rank), int(world), b"".join(handles)))
+
+    def connect_torch(self):
+        """Wire the ranks of the default torch.distributed group (one process per GPU)."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        handles = [None] * world
+        dist.all_gather_object(handles, self.ipc_handle())
+        self.connect(rank, world, handles)
+        dist.barrier()
 
     def order(self):
         out = np.zeros(self.n + 1, dtype=np.int32)

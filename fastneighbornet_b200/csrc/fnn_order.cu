@@ -66,6 +66,8 @@ struct DevState {
     int final3[4];
     // mode-specific selection (Relaxed: written by the host; Random: by k_random_select)
     int mode, mult, fallback, cx_pos, cy_pos;
+    int rank, world;
+    long long run_tag;            // (run counter << 32): makes mailbox tags unique across runs of one context
     int pick_x_id, pick_y_id, pick_kind;
     unsigned long long rng;       // java.util.Random state (48 bits)
     double Dmax;                  // max |D| at load time (slack of the scan's filter, fnn_scan_tma.cuh)
@@ -73,6 +75,14 @@ struct DevState {
 };
 
 struct Partial { double q; unsigned long long key; };
+
+// Multi-GPU selection exchange: every rank scans 1/world of the tiles and posts its partial
+// (Q, i, j) min-loc into slot [iteration parity][rank] of EVERY peer's mailbox with plain stores over
+// NVLink (peer memory mapped through CUDA IPC); the tag carries the iteration number.
+constexpr int MAX_WORLD = 8;
+struct MailSlot { double q; unsigned long long key; long long tag; long long pad; };
+struct Mailbox { MailSlot slot[2][MAX_WORLD]; };
+struct PeerTable { Mailbox* box[MAX_WORLD]; };
 
 #define TWO_THIRDS (2.0 / 3.0)
 
@@ -88,13 +98,15 @@ namespace {
 #include "fnn_modes.cuh"
 
 // ------------------------------------------------------------------ init kernels
-__global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st, int mode, int mult, int fallback, long long seed) {
+__global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st, int mode, int mult, int fallback, long long seed,
+                             int rank, int world, long long run_tag) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) { id[t] = t + 1; pos[t] = t; p2s[t] = t; }
     if (t == 0) {
         memset(st, 0, sizeof(DevState));
         st->m = n; st->c = n; st->P2 = 0; st->num_nodes = n;
         st->mode = mode; st->mult = mult; st->fallback = fallback;
+        st->rank = rank; st->world = world; st->run_tag = run_tag;
         st->rng = ((unsigned long long)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);   // java.util.Random(seed)
     }
 }
@@ -396,7 +408,8 @@ __device__ __forceinline__ double duv_rule(bool uFirst, double dZX, double dYX, 
 constexpr int PICK_THREADS = 1024;
 
 __global__ void __launch_bounds__(PICK_THREADS, 1)
-k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState* st, int* amalg, double* trace, int serial_chain) {
+k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState* st, int* amalg, double* trace, int serial_chain,
+       Mailbox* mail) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[4][CH_TILE] = reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw);
     __shared__ xsum::Smem xs;
@@ -436,6 +449,23 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
         return;
     }
 
+    // ---- multi-GPU: merge the per-rank partial min-locs posted by every rank's scan
+    if (tid == 0 && st->world > 1 && !(st->mode != 0 && m > st->fallback)) {
+        const int par = st->iter & 1;
+        double bq = INFINITY;
+        unsigned long long bk = ~0ull;
+        for (int r = 0; r < st->world; ++r) {
+            volatile MailSlot* ms = &mail->slot[par][r];
+            while (ms->tag != st->run_tag + (long long)st->iter + 1) { }   // posted by rank r's k_scan of this iteration
+            __threadfence_system();
+            const double q = ms->q;
+            const unsigned long long k = ms->key;
+            if (better(q, k, bq, bk)) { bq = q; bk = k; }
+        }
+        st->selQ = bq;
+        st->sel_i = (int)(bk >> 32);
+        st->sel_j = (int)(bk & 0xffffffffu);
+    }
     // ---- Cx, Cy from the scan key; id-order swap (:376-380)
     if (tid == 0) {
         int cx, cy;
@@ -759,6 +789,11 @@ struct fnn_ctx {
     DevState* h_st = nullptr;  // pinned
     CUtensorMap tmap;
     bool have_tmap = false;
+    int rank = 0, world = 1;
+    long long run_counter = 0;
+    Mailbox* mail = nullptr;          // this rank's mailbox (device memory, IPC-exported)
+    PeerTable* peers = nullptr;       // device table of every rank's mailbox (own entry = mail)
+    void* opened[MAX_WORLD] = {nullptr};
     cudaGraphExec_t graph = nullptr;
     int graph_iters = 0;
     bool loaded = false;
@@ -804,6 +839,8 @@ extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
     cudaSetDevice(c->o.device);
     if (c->graph) cudaGraphExecDestroy(c->graph);
     cudaFree(c->D); cudaFree(c->Sx); cudaFree(c->scratch); cudaFree(c->stage); cudaFree(c->trace);
+    for (int r = 0; r < MAX_WORLD; ++r) if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
+    cudaFree(c->mail); cudaFree(c->peers);
     cudaFree(c->id); cudaFree(c->pos); cudaFree(c->p2s); cudaFree(c->amalg); cudaFree(c->st); cudaFree(c->partials);
     if (c->h_st) cudaFreeHost(c->h_st);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -848,6 +885,15 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     FNN_ALLOC(c->p2s, sizeof(int) * c->ld);
     FNN_ALLOC(c->amalg, sizeof(int) * 5 * (2 * n + 8));
     FNN_ALLOC(c->st, sizeof(DevState));
+    FNN_ALLOC(c->mail, sizeof(Mailbox));
+    FNN_ALLOC(c->peers, sizeof(PeerTable));
+    FNN_CUDA(cudaMemset(c->mail, 0, sizeof(Mailbox)));
+    {
+        PeerTable pt;
+        memset(&pt, 0, sizeof(pt));
+        pt.box[0] = c->mail;
+        FNN_CUDA(cudaMemcpy(c->peers, &pt, sizeof(pt), cudaMemcpyHostToDevice));
+    }
     c->scan_grid = c->sms * 2;
     c->row_grid = std::max<int>(1, std::min<int64_t>((n + 255) / 256, c->sms * 4));
     FNN_ALLOC(c->partials, sizeof(Partial) * c->scan_grid);
@@ -923,7 +969,7 @@ static_assert(PICK_THREADS == xsum::THREADS, "exact-sum block size");
 
 static inline void launch_scan(fnn_ctx* c) {
     if (c->have_tmap)
-        tma::k_scan_tma<<<c->sms, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials);
+        tma::k_scan_tma<<<c->sms, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials, c->peers);
     else
         k_scan<32><<<c->scan_grid, SCAN_THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->partials);
 }
@@ -952,7 +998,7 @@ static inline void launch_rest(fnn_ctx* c) {
     if (c->o.mode >= FNN_RANDOM_N)
         modes::k_random_select<<<1, modes::THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->p2s, c->st);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
-                                                    c->o.reserved[1] != 2);
+                                                    c->o.reserved[1] != 2, c->mail);
     k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
     k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage);
     k_chain<<<1, PICK_THREADS, CHAIN_SMEM, c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage, c->o.reserved[1] != 2);
@@ -1147,7 +1193,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     FNN_CUDA(cudaEventRecord(e0, c->stream));
     const int ni = (int)n;
     k_init_nodes<<<(ni + 255) / 256, 256, 0, c->stream>>>(ni, c->id, c->pos, c->p2s, c->st, c->o.mode, c->o.mult,
-                                                          c->o.canonical_fallback, (long long)c->o.seed);
+                                                          c->o.canonical_fallback, (long long)c->o.seed, c->rank, c->world, (long long)(++c->run_counter) << 32);
     k_rowsum<<<(ni + 127) / 128, 128, 0, c->stream>>>(c->D, c->ld, ni, c->Sx, c->st);
     FNN_CUDA(cudaGetLastError());
     int64_t launches = 2, scans = 0;
@@ -1310,5 +1356,40 @@ extern "C" int fnn_seq_sum(const fnn_opts* o, const double* rows, int32_t nrows,
     }
     FNN_CUDA(cudaMemcpy(out, d_out, sizeof(double) * nrows, cudaMemcpyDeviceToHost));
     cudaFree(d_rows); cudaFree(d_out);
+    return FNN_OK;
+}
+
+// ---- multi-GPU wiring: one process per GPU; the host language layer moves the 64-byte IPC handles
+extern "C" int fnn_ctx_ipc_handle(fnn_ctx* c, void* handle_out) {
+    if (!c || !handle_out) { fnn::set_error("fnn_ctx_ipc_handle: null argument"); return FNN_E_ARG; }
+    FNN_CUDA(cudaSetDevice(c->o.device));
+    cudaIpcMemHandle_t h;
+    FNN_CUDA(cudaIpcGetMemHandle(&h, c->mail));
+    memcpy(handle_out, &h, sizeof(h));
+    return FNN_OK;
+}
+
+extern "C" int fnn_ctx_connect(fnn_ctx* c, int32_t rank, int32_t world, const void* handles) {
+    if (!c || !handles || world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) {
+        fnn::set_error("fnn_ctx_connect: need 0 <= rank < world <= %d", MAX_WORLD);
+        return FNN_E_ARG;
+    }
+    if (!c->have_tmap) { fnn::set_error("fnn_ctx_connect: the sharded scan needs the TMA selection kernel"); return FNN_E_UNSUPPORTED; }
+    FNN_CUDA(cudaSetDevice(c->o.device));
+    PeerTable pt;
+    memset(&pt, 0, sizeof(pt));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { pt.box[r] = c->mail; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        FNN_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->opened[r] = p;
+        pt.box[r] = (Mailbox*)p;
+    }
+    FNN_CUDA(cudaMemcpy(c->peers, &pt, sizeof(pt), cudaMemcpyHostToDevice));
+    c->rank = rank;
+    c->world = world;
+    if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
     return FNN_OK;
 }

@@ -196,7 +196,7 @@ __device__ __forceinline__ void eval_pp(const double* sm, const RowData* rd, dou
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ Sx, const int* __restrict__ pos,
-           DevState* st, Partial* partials) {
+           DevState* st, Partial* partials, const PeerTable* peers) {
     if (st->done || (st->mode != 0 && st->m > st->fallback)) return;   // NetMakerOriginal.java:361-366
     extern __shared__ __align__(1024) unsigned char smem[];
     // keep the ring pointer in the shared window (no generic-address loads): offset, not integer cast
@@ -227,7 +227,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
         if (tid == CONSUMERS) {
             int stage = 0;
             uint32_t phase = 0;
-            for (TileIter it(m, blockIdx.x, gridDim.x); it.valid(); it.next()) {
+            for (TileIter it(m, st->rank + st->world * blockIdx.x, st->world * gridDim.x); it.valid(); it.next()) {
                 int r0, cb0;
                 it.decode(r0, cb0);
                 const int rEnd = min(r0 + TILE_ROWS, m);
@@ -251,7 +251,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
         const int box = gt >> 7, lc = (gt & 127) * 2;   // which box of the stage, local column
         const int uo = grp * RPG;                       // first chunk row of this group
         int tileParity = 0;
-        for (TileIter it(m, blockIdx.x, gridDim.x); it.valid(); it.next(), tileParity ^= 1) {
+        for (TileIter it(m, st->rank + st->world * blockIdx.x, st->world * gridDim.x); it.valid(); it.next(), tileParity ^= 1) {
             int r0, cb0;
             it.decode(r0, cb0);
             const int rEnd = min(r0 + TILE_ROWS, m);
@@ -379,10 +379,26 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
         if (tid == 0) {
             for (int w = 1; w < THREADS / 32; ++w)
                 if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
-            st->selQ = bq;
-            st->sel_i = (int)(bk >> 32);
-            st->sel_j = (int)(bk & 0xffffffffu);
             st->ticket = 0;
+            if (st->world > 1) {
+                // post this rank's partial into every rank's mailbox (own included); k_pick merges
+                const int par = st->iter & 1;
+                for (int r = 0; r < st->world; ++r) {
+                    volatile MailSlot* ms = &peers->box[r]->slot[par][st->rank];
+                    ms->q = bq;
+                    ms->key = bk;
+                }
+                __threadfence_system();
+                for (int r = 0; r < st->world; ++r) {
+                    volatile MailSlot* ms = &peers->box[r]->slot[par][st->rank];
+                    ms->tag = st->run_tag + (long long)st->iter + 1;
+                }
+                __threadfence_system();
+            } else {
+                st->selQ = bq;
+                st->sel_i = (int)(bk >> 32);
+                st->sel_j = (int)(bk & 0xffffffffu);
+            }
         }
     }
 }

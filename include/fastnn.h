@@ -97,6 +97,15 @@ int fnn_ctx_stats(fnn_ctx* c, fnn_stats* out);
 /* device pointer + leading dimension of the internal matrix (for zero-copy producers such as torch) */
 int fnn_ctx_matrix_ptr(fnn_ctx* c, double** dptr, int64_t* ld);
 
+/* ---- multi-GPU (one process per GPU) --------------------------------------------
+ * The selection scan is sharded: rank r scans every world-th tile of the lower triangle and the per-rank
+ * (Q,i,j) partial min-locs are exchanged through peer-mapped mailboxes over NVLink inside the kernels.
+ * State and matrix are replicated (every rank loads the same matrix and returns the same ordering).
+ * fnn_ctx_ipc_handle writes this rank's 64-byte CUDA IPC handle; the host layer all-gathers the handles
+ * (torch.distributed / MPI / files) and passes the world*64 bytes, rank-ordered, to fnn_ctx_connect. */
+int fnn_ctx_ipc_handle(fnn_ctx* c, void* handle_out /* 64 bytes */);
+int fnn_ctx_connect(fnn_ctx* c, int32_t rank, int32_t world, const void* handles /* world * 64 bytes */);
+
 /* ---- one-shot seams ----------------------------------------------------------------- */
 /* B1: replaces `new NeighborNetX(D, n, ...).runNeighborNet()`.  Exactly one of D_rowmajor
  * (host, n*n) or phylip_path must be non-NULL.  n<=3 returns the identity ordering
