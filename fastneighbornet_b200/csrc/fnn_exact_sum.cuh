@@ -2,7 +2,7 @@
 //
 // The reference accumulates ComputeRx (NetMakerOriginal.java:549-561) and u.Sx (:530-535) with
 // `sum += x` in position order; those bits feed later argmins, so the rounding sequence must be
-// reproduced, and a dependent DADD chain costs ~4.8 ns per element on one lane.
+// reproduced, and a dependent DADD chain costs ~5 ns per element on one lane.
 //
 // Observation: while the running sum s stays inside one binade [2^e, 2^(e+1)) and the addends
 // are non-negative, every step is s <- s + RN_ulp(a) with ulp = 2^(e-52), i.e. INTEGER addition
@@ -10,157 +10,227 @@
 // case where the increment depends on s, via round-to-even).  Integer addition is associative, so
 // a run of such steps collapses to one add of the pre-summed increments.
 //
-// Algorithm per 4096-element tile (1024 threads x 4 consecutive elements):
-//   1. approximate prefix sums (any order) place each 4-element chunk in a binade e;
-//   2. each chunk whose whole uncertainty interval lies in one binade and whose elements are
-//      non-negative, normal (or zero), not ties, gets the integer increment C = sum R(a);
-//      chunk -> warp -> tile summaries (all members same e) are combined by shuffles;
-//   3. one walker lane per chain applies summaries top-down.  Every application is VERIFIED
-//      exactly: exponent(s) == e before, significand + C < 2^53 after.  Because increments are
-//      non-negative, that proves no step of the run left the binade, hence the collapsed result
-//      equals the sequential one bit for bit.  Anything unverifiable (binade crossings, ties,
-//      negative / subnormal / non-finite addends, s == 0) falls back to plain sequential adds
-//      of that chunk.  The approximation only steers efficiency, never the result.
+// Algorithm (one block of 1024 threads, one pass over the chain):
+//   A. thread t owns the contiguous segment [t*L, (t+1)*L); an approximate prefix sum (any order)
+//      places the segment in a binade e; if its whole uncertainty interval lies in that binade and
+//      its elements are non-negative, finite and not ties, the segment gets the integer increment
+//      C = sum rint(a * 2^(52-e)) (exact in fp64 while < 2^53).  32 segments combine to a warp
+//      summary when they agree on e.
+//   B. one warp per chain walks: 32 warp summaries -> 32 segment summaries of a failing warp ->
+//      the elements of a failing segment (plain sequential adds).  At the two upper levels the
+//      warp applies the longest applicable PREFIX of the 32 summaries in one cooperative step.
+//      Every application is VERIFIED exactly: exponent(s) == e before, significand + C < 2^53
+//      after.  Because increments are non-negative, that proves no step of the run left the
+//      binade, hence the collapsed result equals the sequential one bit for bit.  Whatever is
+//      not verifiable (binade crossings, ties, negative / non-finite addends, s == 0) is summed
+//      sequentially.  The approximation only steers efficiency, never the result.
 #pragma once
 
 namespace xsum {
 
 constexpr int THREADS = 1024;
-constexpr int L = 4;                 // elements per thread
-constexpr int TILE = THREADS * L;    // 4096
+constexpr int LEAF_MAX = 128;        // max segment length (chains up to 131072 elements)
+constexpr double TWO53 = 9007199254740992.0;
 constexpr unsigned long long M52 = (1ull << 52) - 1;
-constexpr unsigned long long B53 = 1ull << 53;
-
-// summary word: 0 = not collapsible; else (biased exponent << 53) | increment (< 2^53)
-__device__ __forceinline__ unsigned long long chunk_summary(const double* a, double pstart, double pend) {
-    const double eps = 3.7e-12;   // >= 2^-38: bounds the error of the approximate in-tile prefix
-    if (!(pstart > 0.0)) return 0;
-    const unsigned long long lo = (unsigned long long)__double_as_longlong(pstart * (1.0 - eps));
-    const unsigned long long hi = (unsigned long long)__double_as_longlong(pend * (1.0 + eps));
-    const unsigned long long eb = (lo >> 52) & 0x7ff;
-    if (eb == 0 || eb == 0x7ff || ((hi >> 52) & 0x7ff) != eb || (lo >> 63)) return 0;
-    unsigned long long C = 0;
-#pragma unroll
-    for (int j = 0; j < L; ++j) {
-        const unsigned long long b = (unsigned long long)__double_as_longlong(a[j]);
-        if ((b << 1) == 0) continue;                       // +-0
-        const unsigned long long ea = (b >> 52) & 0x7ff;
-        if ((b >> 63) || ea == 0 || ea == 0x7ff || ea > eb) return 0;   // negative, subnormal, inf/nan, too large
-        const unsigned long long ma = (b & M52) | (1ull << 52);
-        const unsigned sh = (unsigned)(eb - ea);
-        if (sh == 0) C += ma;
-        else if (sh <= 53) {
-            const unsigned long long half = 1ull << (sh - 1);
-            const unsigned long long rem = ma & ((half << 1) - 1);
-            if (rem == half) return 0;                     // tie: increment depends on the parity of s
-            C += (ma >> sh) + (rem > half ? 1ull : 0ull);
-        }                                                  // sh >= 54: a < ulp/2, increment 0
-    }
-    if (C >= B53) return 0;
-    return (eb << 53) | C;
-}
-
-// combine 32 lane summaries of one warp: collapsible iff all are and all share the exponent
-__device__ __forceinline__ unsigned long long warp_combine(unsigned long long w) {
-    const unsigned long long e0 = __shfl_sync(0xffffffffu, w, 0) >> 53;
-    const bool ok = __all_sync(0xffffffffu, w != 0 && (w >> 53) == e0);
-    unsigned long long c = w & (B53 - 1);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-    return (ok && c < B53) ? ((e0 << 53) | c) : 0ull;
-}
-
-__device__ __forceinline__ bool try_apply(double& s, unsigned long long w) {
-    if (w == 0) return false;
-    const unsigned long long b = (unsigned long long)__double_as_longlong(s);
-    if ((b >> 52) != (w >> 53)) return false;              // sign bit set or different binade
-    const unsigned long long tot = ((b & M52) | (1ull << 52)) + (w & (B53 - 1));
-    if (tot >= B53) return false;                          // would leave the binade
-    s = __longlong_as_double((long long)(((w >> 53) << 52) | (tot & M52)));
-    return true;
-}
+constexpr int E_INVALID = 0, E_IDENT = -1;   // summary exponent codes (else: biased exponent 1..2046)
 
 struct Smem {
-    double carry[4];
     double wtot[4][32];
-    unsigned long long wsum[4][32];
-    unsigned long long csum[4][THREADS];
+    double wC[4][32];
+    int wE[4][32];
+    double cC[4][THREADS];
+    int cE[4][THREADS];
+    double leaf[4][LEAF_MAX];
+    double result[4];
 };
 
-// buf: [NR][TILE] doubles of dynamic shared memory; sm: scratch above.  All THREADS threads call.
-// load(r, i) returns element i of chain r (only called for i < len).  out[r] = sequential sum.
-template <int NR, typename Loader>
-__device__ void block_exact_seq_sum(double (*buf)[TILE], Smem* sm, int len, Loader load, double* out) {
+// longest applicable prefix of the 32 lane summaries (lanes < start are already consumed).
+// s is uniform across the warp.  Returns the index of the first summary that was NOT applied.
+__device__ __forceinline__ int coop_apply(double& s, int e_lane, double C_lane, int start, int lane) {
+    double P = (lane >= start && e_lane > 0) ? C_lane : 0.0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, P, off);
+        if (lane >= off) P += t;
+    }
+    const unsigned long long b = (unsigned long long)__double_as_longlong(s);
+    const int es = (int)(b >> 52);                         // sign bit set -> never equals a summary exponent
+    const double msd = (double)((b & M52) | (1ull << 52));
+    const bool structural = (lane < start) || e_lane == E_IDENT || (e_lane > 0 && e_lane == es);
+    const unsigned bad = ~__ballot_sync(0xffffffffu, structural);
+    const int f = bad ? (__ffs(bad) - 1) : 32;
+    const bool ok = lane >= start && lane < f && (msd + P < TWO53);
+    const int p = __popc(__ballot_sync(0xffffffffu, ok));   // ok lanes form a contiguous run from `start` (P is monotone)
+    if (p > 0) {
+        const double Pp = __shfl_sync(0xffffffffu, P, start + p - 1);
+        if (Pp > 0.0) {
+            const unsigned long long tot = (unsigned long long)(msd + Pp);
+            s = __longlong_as_double((long long)(((unsigned long long)es << 52) | (tot & M52)));
+        }
+    }
+    return start + p;
+}
+
+// buf unused (kept for the serial variant's signature symmetry).  All THREADS threads call.
+// load(r, i): element i of chain r; present(r): whether chain r exists; out[r] = sequential sum.
+template <int NR, typename Loader, typename Present>
+__device__ void block_exact_seq_sum(Smem* sm, int len, Loader load, Present present, double* out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < NR) sm->carry[tid] = 0.0;
-    __syncthreads();
-    for (int base = 0; base < len; base += TILE) {
-        long long t0_ = clock64();
-        double a[NR][L], ls[NR], incl[NR];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-#pragma unroll
-            for (int j = 0; j < L; ++j) {
-                const int i = base + tid * L + j;
-                a[r][j] = (i < len) ? load(r, i) : 0.0;
-                buf[r][tid * L + j] = a[r][j];
-            }
-            ls[r] = ((a[r][0] + a[r][1]) + a[r][2]) + a[r][3];
-            double v = ls[r];
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, v, off);
-                if (lane >= off) v += t;
-            }
-            incl[r] = v;
-            if (lane == 31) sm->wtot[r][warp] = v;
-        }
-        __syncthreads();
-        if (warp < NR) {   // warp r turns the 32 warp totals of chain r into exclusive offsets
-            double v = sm->wtot[warp][lane];
-            const double own = v;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, v, off);
-                if (lane >= off) v += t;
-            }
-            sm->wtot[warp][lane] = v - own;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const double pstart = sm->carry[r] + (sm->wtot[r][warp] + (incl[r] - ls[r]));
-            const unsigned long long cs = chunk_summary(a[r], pstart, pstart + ls[r]);
-            sm->csum[r][tid] = cs;
-            const unsigned long long ws = warp_combine(cs);
-            if (lane == 0) sm->wsum[r][warp] = ws;
-        }
-        __syncthreads();
-        long long t1_ = clock64();
-        if (warp < NR) {   // warp r walks chain r through this tile
-            const int r = warp;
-            const unsigned long long tsum = warp_combine(sm->wsum[r][lane]);
-            if (lane == 0) {
-                double s = sm->carry[r];
-                if (!try_apply(s, tsum)) {
-                    for (int w = 0; w < 32; ++w) {
-                        if (try_apply(s, sm->wsum[r][w])) continue;
-                        for (int t = w * 32; t < w * 32 + 32; ++t) {
-                            if (try_apply(s, sm->csum[r][t])) continue;
-                            const double* e = &buf[r][t * L];
-                            s += e[0]; s += e[1]; s += e[2]; s += e[3];
-                        }
-                    }
-                }
-                sm->carry[r] = s;
-            }
-        }
-        __syncthreads();
+    const int L = (len + THREADS - 1) / THREADS;            // <= LEAF_MAX
+    const int i0 = min(tid * L, len), i1 = min(i0 + L, len);
+    // ---- A1: local sums -> approximate exclusive prefix
 #ifdef FNN_XSUM_TIMING
-        if (tid == 0) printf("tile base=%d prep=%lld walk=%lld cycles\n", base, t1_ - t0_, clock64() - t1_);
+    long long t0_ = clock64();
+#endif
+    double ls[NR], incl[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) ls[r] = 0.0;
+    for (int i = i0; i < i1; i += 4) {   // 4 x NR independent loads in flight
+        double a[NR][4];
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[r][q] = (present(r) && i + q < i1) ? load(r, i + q) : 0.0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) ls[r] += (a[r][0] + a[r][1]) + (a[r][2] + a[r][3]);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double v = ls[r];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off) v += t;
+        }
+        incl[r] = v;
+        if (lane == 31) sm->wtot[r][warp] = v;
+    }
+    __syncthreads();
+    if (warp < NR) {
+        double v = sm->wtot[warp][lane];
+        const double own = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off) v += t;
+        }
+        sm->wtot[warp][lane] = v - own;
+    }
+    __syncthreads();
+#ifdef FNN_XSUM_TIMING
+    long long t1_ = clock64();
+#endif
+    // ---- A2: segment summaries, warp summaries
+    {
+        int eb[NR];
+        double scale[NR], C[NR];
+        bool bad[NR], anynz[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const double pstart = sm->wtot[r][warp] + (incl[r] - ls[r]);
+            const double pend = pstart + ls[r];
+            const double eps = 4.0e-11;   // >> error of the approximate prefix (<= ~2^17 terms, tree order)
+            const unsigned long long lo = (unsigned long long)__double_as_longlong(pstart * (1.0 - eps));
+            const unsigned long long hi = (unsigned long long)__double_as_longlong(pend * (1.0 + eps));
+            eb[r] = (int)(lo >> 52);
+            bad[r] = !(pstart > 0.0) || eb[r] != (int)(hi >> 52) || eb[r] < 123 || eb[r] > 1923;
+            scale[r] = __longlong_as_double((long long)(2098 - min(max(eb[r], 123), 1923)) << 52);   // 2^(52 - e)
+            C[r] = 0.0;
+            anynz[r] = false;
+        }
+        for (int i = i0; i < i1; i += 4) {
+            double a[NR][4];
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[r][q] = (present(r) && i + q < i1) ? load(r, i + q) : 0.0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double x = a[r][q] * scale[r];
+                    const double R = rint(x);
+                    bad[r] |= (a[r][q] < 0.0) | (fabs(x - R) == 0.5);
+                    anynz[r] |= (a[r][q] != 0.0);
+                    C[r] += R;
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            int e;
+            double Cr = C[r];
+            if (!present(r) || i1 <= i0 || !anynz[r]) { e = E_IDENT; Cr = 0.0; }
+            else if (bad[r] || !(Cr < TWO53)) { e = E_INVALID; Cr = 0.0; }
+            else e = eb[r];
+            sm->cE[r][tid] = e;
+            sm->cC[r][tid] = Cr;
+            // warp summary: all segments applicable and agreeing on the binade (identities are neutral)
+            const unsigned real = __ballot_sync(0xffffffffu, e > 0);
+            const int e0 = real ? __shfl_sync(0xffffffffu, e, __ffs(real) - 1) : E_IDENT;
+            const bool agree = __all_sync(0xffffffffu, e == E_IDENT || e == e0);
+            double c = Cr;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+            if (lane == 0) {
+                const bool okw = agree && (c < TWO53);
+                sm->wE[r][warp] = okw ? e0 : E_INVALID;
+                sm->wC[r][warp] = okw ? c : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+#ifdef FNN_XSUM_TIMING
+    long long t2_ = clock64();
+    int ncoop_ = 0, nleaf_ = 0;
+#endif
+    // ---- B: warp r walks chain r
+    if (warp < NR) {
+        const int r = warp;
+        double s = 0.0;
+        if (present(r)) {
+            const int we = sm->wE[r][lane];
+            const double wc = sm->wC[r][lane];
+            int s2 = 0;
+            while (s2 < 32) {
+                s2 = coop_apply(s, we, wc, s2, lane);
+#ifdef FNN_XSUM_TIMING
+                ++ncoop_;
+#endif
+                if (s2 >= 32) break;
+                const int w = s2;                              // warp summary w is not applicable: open it
+                const int te = sm->cE[r][w * 32 + lane];
+                const double tc = sm->cC[r][w * 32 + lane];
+                int s1 = 0;
+                while (s1 < 32) {
+                    s1 = coop_apply(s, te, tc, s1, lane);
+#ifdef FNN_XSUM_TIMING
+                    ++ncoop_; if (s1 < 32) ++nleaf_;
+#endif
+                    if (s1 >= 32) break;
+                    const int t = w * 32 + s1;                 // segment t is not applicable: plain sequential adds
+                    const int j0 = min(t * L, len), j1 = min(j0 + L, len);
+                    for (int k = lane; k < j1 - j0; k += 32) sm->leaf[r][k] = load(r, j0 + k);
+                    __syncwarp();
+                    const double* e = sm->leaf[r];
+                    int k = 0;
+                    for (; k + 4 <= j1 - j0; k += 4) {
+                        const double v0 = e[k], v1 = e[k + 1], v2 = e[k + 2], v3 = e[k + 3];
+                        s += v0; s += v1; s += v2; s += v3;
+                    }
+                    for (; k < j1 - j0; ++k) s += e[k];
+                    __syncwarp();
+                    s1 += 1;
+                }
+                s2 += 1;
+            }
+        }
+        if (lane == 0) sm->result[r] = s;
+#ifdef FNN_XSUM_TIMING
+        if (lane == 0) printf("chain %d: A1=%lld A2=%lld walk=%lld cycles, coop=%d leaf=%d L=%d\n", r, t1_ - t0_, t2_ - t1_, clock64() - t2_, ncoop_, nleaf_, L);
 #endif
     }
-    if (tid < NR) out[tid] = sm->carry[tid];
+    __syncthreads();
+    if (tid < NR) out[tid] = sm->result[tid];
     __syncthreads();
 }
 

@@ -346,6 +346,8 @@ k_scan(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, 
 // All threads stage tiles into shared memory through `load(row, i)`; lane r of warp 0 owns
 // chain r.  Double-buffered so the staging of tile k+1 overlaps the dependent adds of tile k.
 constexpr int CH_TILE = 1024;
+constexpr size_t PICK_SMEM = sizeof(xsum::Smem) > 2 * 4 * CH_TILE * sizeof(double) ? sizeof(xsum::Smem) : 2 * 4 * CH_TILE * sizeof(double);
+constexpr size_t CHAIN_SMEM = PICK_SMEM;
 
 template <int NR, typename Loader>
 __device__ void block_seq_sum(double (*buf)[NR][CH_TILE], int len, Loader load, double* out /*[NR]*/) {
@@ -412,7 +414,6 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
        Mailbox* mail) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[4][CH_TILE] = reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw);
-    __shared__ xsum::Smem xs;
     __shared__ int sh[8];
     __shared__ double rx[4];
     if (st->done) return;
@@ -491,7 +492,7 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
             return full ? v : v * 0.5;
         };
         if (serial_chain) block_seq_sum<4>(buf, m, load, rx);
-        else xsum::block_exact_seq_sum<4>(reinterpret_cast<double (*)[xsum::TILE]>(smem_raw), &xs, m, load, rx);
+        else xsum::block_exact_seq_sum<4>(reinterpret_cast<xsum::Smem*>(smem_raw), m, load, [&](int r) { return zs[r] >= 0; }, rx);
     } else {
         if (tid < 4) rx[tid] = 0.0;
         __syncthreads();
@@ -737,13 +738,12 @@ __global__ void __launch_bounds__(PICK_THREADS, 1)
 k_chain(double* Sx, const int* id, const int* p2s, DevState* st, const double* __restrict__ stage, int serial_chain) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[1][CH_TILE] = reinterpret_cast<double (*)[1][CH_TILE]>(smem_raw);
-    __shared__ xsum::Smem xs;
     __shared__ double tot[1];
     if (st->done || st->skip) return;
     const int m_new = st->m_new;
     auto load = [&](int, int i) -> double { return stage[i]; };
     if (serial_chain) block_seq_sum<1>(buf, m_new, load, tot);
-    else xsum::block_exact_seq_sum<1>(reinterpret_cast<double (*)[xsum::TILE]>(smem_raw), &xs, m_new, load, tot);
+    else xsum::block_exact_seq_sum<1>(reinterpret_cast<xsum::Smem*>(smem_raw), m_new, load, [](int) { return true; }, tot);
     if (threadIdx.x == 0) {
         const int su = st->su;
         Sx[su] = tot[0];
@@ -761,11 +761,10 @@ k_chain(double* Sx, const int* id, const int* p2s, DevState* st, const double* _
 __global__ void __launch_bounds__(PICK_THREADS, 1)
 k_seqsum(const double* __restrict__ rows, int64_t stride, int nrows, int len, double* out, int serial_chain) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ xsum::Smem xs;
     __shared__ double res[4];
     auto load = [&](int r, int i) -> double { return r < nrows ? rows[(int64_t)r * stride + i] : 0.0; };
     if (serial_chain) block_seq_sum<4>(reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw), len, load, res);
-    else xsum::block_exact_seq_sum<4>(reinterpret_cast<double (*)[xsum::TILE]>(smem_raw), &xs, len, load, res);
+    else xsum::block_exact_seq_sum<4>(reinterpret_cast<xsum::Smem*>(smem_raw), len, load, [&](int r) { return r < nrows; }, res);
     if (threadIdx.x < nrows) out[threadIdx.x] = res[threadIdx.x];
 }
 
@@ -791,6 +790,7 @@ struct fnn_ctx {
     bool have_tmap = false;
     int rank = 0, world = 1;
     long long run_counter = 0;
+    int serial_chain = 0;             // 1: one-lane dependent chain instead of the collapsed exact summation
     Mailbox* mail = nullptr;          // this rank's mailbox (device memory, IPC-exported)
     PeerTable* peers = nullptr;       // device table of every rank's mailbox (own entry = mail)
     void* opened[MAX_WORLD] = {nullptr};
@@ -862,6 +862,7 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     fnn_ctx* c = new fnn_ctx();
     c->o = *o;
     c->n = n;
+    c->serial_chain = (o->reserved[1] == 1) || n > (int64_t)xsum::THREADS * xsum::LEAF_MAX;
     c->ld = (n + 15) / 16 * 16;
     cudaDeviceProp prop;
     FNN_CUDA(cudaGetDeviceProperties(&prop, o->device));
@@ -900,8 +901,8 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     if (o->record_trace) FNN_ALLOC(c->trace, sizeof(double) * 8 * (n + 8));
     FNN_CUDA(cudaMallocHost((void**)&c->h_st, sizeof(DevState)));
     FNN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    FNN_CUDA(cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * xsum::TILE * sizeof(double))));
-    FNN_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1 * xsum::TILE * sizeof(double))));
+    FNN_CUDA(cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICK_SMEM));
+    FNN_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
     c->scan_grid = std::max(c->scan_grid, c->sms);
     if (o->reserved[0] == 0) {  // reserved[0] = 1 selects the register-tiled scan (A/B only)
         int trc = make_tensor_map(c);
@@ -963,8 +964,6 @@ extern "C" int fnn_ctx_matrix_ptr(fnn_ctx* c, double** dptr, int64_t* ld) {
     return FNN_OK;
 }
 
-constexpr size_t PICK_SMEM = 4 * xsum::TILE * sizeof(double);   // >= 2*4*CH_TILE doubles of the serial variant
-constexpr size_t CHAIN_SMEM = 1 * xsum::TILE * sizeof(double);
 static_assert(PICK_THREADS == xsum::THREADS, "exact-sum block size");
 
 static inline void launch_scan(fnn_ctx* c) {
@@ -998,10 +997,10 @@ static inline void launch_rest(fnn_ctx* c) {
     if (c->o.mode >= FNN_RANDOM_N)
         modes::k_random_select<<<1, modes::THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->p2s, c->st);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
-                                                    c->o.reserved[1] != 2, c->mail);
+                                                    c->serial_chain, c->mail);
     k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
     k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage);
-    k_chain<<<1, PICK_THREADS, CHAIN_SMEM, c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage, c->o.reserved[1] != 2);
+    k_chain<<<1, PICK_THREADS, CHAIN_SMEM, c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage, c->serial_chain);
 }
 
 
@@ -1330,7 +1329,7 @@ int64_t fnn_ctx_n_(fnn_ctx* c) { return c->n; }
 void fnn_ctx_mark_loaded_(fnn_ctx* c) { c->loaded = true; }
 
 extern "C" int fnn_seq_sum(const fnn_opts* o, const double* rows, int32_t nrows, int64_t len, double* out) {
-    if (!rows || !out || nrows < 1 || nrows > 4 || len < 0 || len > 0x7fffffff) { fnn::set_error("fnn_seq_sum: bad arguments"); return FNN_E_ARG; }
+    if (!rows || !out || nrows < 1 || nrows > 4 || len < 0 || len > (int64_t)xsum::THREADS * xsum::LEAF_MAX) { fnn::set_error("fnn_seq_sum: bad arguments"); return FNN_E_ARG; }
     int rc = ensure_device(o);
     if (rc) return rc;
     double *d_rows = nullptr, *d_out = nullptr;

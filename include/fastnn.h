@@ -53,8 +53,8 @@ typedef struct fnn_opts {
     int32_t use_graph;          /* 1: replay the per-iteration kernel sequence as a CUDA graph */
     int32_t record_trace;       /* 1: keep the per-iteration (m,c,Cx,Cy,x,y,kind,best) trace on device */
     int32_t profile_every;      /* >0: time the selection kernel of every k-th iteration with CUDA events */
-    int32_t reserved[6];        /* [0]=1: register-tiled scan instead of the TMA pipeline (A/B); [1]=2: collapse the
-                                   sequential chains with the exact parallel summation (experimental, slower today) */
+    int32_t reserved[6];        /* [0]=1: register-tiled scan instead of the TMA pipeline (A/B); [1]=1: sum the
+                                   sequential chains on one lane instead of the collapsed exact summation (A/B) */
 } fnn_opts;
 
 typedef struct fnn_ctx fnn_ctx; /* opaque: device matrix + node tables for one problem of n taxa */
