@@ -281,7 +281,7 @@ def main():
         pctx.close()
         peak, peak_src = measured_peak()
         achieved = ps["prof_scan_bytes"] / (ps["prof_scan_ms"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_scan<32>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        roofline = {"bound": "hbm", "kernel": "k_scan_tma", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "samples": ps["prof_scan_samples"],
                     "avg_launch_ms": ps["prof_scan_ms"] / max(1, ps["prof_scan_samples"]),
                     "alg_bytes_per_launch": ps["prof_scan_bytes"] / max(1, ps["prof_scan_samples"]),
