@@ -72,7 +72,9 @@ __device__ __forceinline__ int coop_apply(double& s, int e_lane, double C_lane, 
 }
 
 // buf unused (kept for the serial variant's signature symmetry).  All THREADS threads call.
-// load(r, i): element i of chain r; present(r): whether chain r exists; out[r] = sequential sum.
+// load(r, t, k): element k of segment t (= element t*L + k) of chain r, with L = ceil(len/1024) - callers may store
+// chains segment-transposed so that the 32 lanes of a warp read consecutive addresses; present(r): whether chain r
+// exists; out[r] = sequential sum.
 template <int NR, typename Loader, typename Present>
 __device__ void block_exact_seq_sum(Smem* sm, int len, Loader load, Present present, double* out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -90,7 +92,7 @@ __device__ void block_exact_seq_sum(Smem* sm, int len, Loader load, Present pres
 #pragma unroll
         for (int r = 0; r < NR; ++r)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) a[r][q] = (present(r) && i + q < i1) ? load(r, i + q) : 0.0;
+            for (int q = 0; q < 4; ++q) a[r][q] = (present(r) && i + q < i1) ? load(r, tid, i + q - i0) : 0.0;
 #pragma unroll
         for (int r = 0; r < NR; ++r) ls[r] += (a[r][0] + a[r][1]) + (a[r][2] + a[r][3]);
     }
@@ -143,7 +145,7 @@ __device__ void block_exact_seq_sum(Smem* sm, int len, Loader load, Present pres
 #pragma unroll
             for (int r = 0; r < NR; ++r)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) a[r][q] = (present(r) && i + q < i1) ? load(r, i + q) : 0.0;
+                for (int q = 0; q < 4; ++q) a[r][q] = (present(r) && i + q < i1) ? load(r, tid, i + q - i0) : 0.0;
 #pragma unroll
             for (int r = 0; r < NR; ++r)
 #pragma unroll
@@ -209,7 +211,7 @@ __device__ void block_exact_seq_sum(Smem* sm, int len, Loader load, Present pres
                     if (s1 >= 32) break;
                     const int t = w * 32 + s1;                 // segment t is not applicable: plain sequential adds
                     const int j0 = min(t * L, len), j1 = min(j0 + L, len);
-                    for (int k = lane; k < j1 - j0; k += 32) sm->leaf[r][k] = load(r, j0 + k);
+                    for (int k = lane; k < j1 - j0; k += 32) sm->leaf[r][k] = load(r, t, k);
                     __syncwarp();
                     const double* e = sm->leaf[r];
                     int k = 0;

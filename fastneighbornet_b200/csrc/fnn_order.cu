@@ -69,6 +69,7 @@ struct DevState {
     int rank, world;
     long long run_tag;            // (run counter << 32): makes mailbox tags unique across runs of one context
     int pick_x_id, pick_y_id, pick_kind;
+    int cx, cxn, cy, cyn, need_rx;   // k_select: chosen clusters (slots) and whether ComputeRx is needed
     unsigned long long rng;       // java.util.Random state (48 bits)
     double Dmax;                  // max |D| at load time (slack of the scan's filter, fnn_scan_tma.cuh)
     double alg_bytes;             // running sum of the selection scan's algorithmic bytes
@@ -406,15 +407,72 @@ __device__ __forceinline__ double duv_rule(bool uFirst, double dZX, double dYX, 
     return TWO_THIRDS * B + dYX / 3.0;
 }
 
+// ------------------------------------------------------------------ K3a: selection result -> clusters (one warp)
+// Multi-GPU: merges the per-rank partial min-locs posted by every rank's scan.  Then Cx, Cy from the
+// (i, j) key (or from the Relaxed/Random strategy), the id-order swap of NetMakerOriginal.java:376-380.
+__global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
+    if (st->done || threadIdx.x != 0) return;
+    const int m = st->m, P2 = st->P2;
+    if (m == 4 && st->c == 2) { st->need_rx = 0; return; }   // special case is handled by k_pick
+    const bool strategy = (st->mode != 0 && m > st->fallback);
+    if (st->world > 1 && !strategy) {
+        const int par = st->iter & 1;
+        double bq = INFINITY;
+        unsigned long long bk = ~0ull;
+        for (int r = 0; r < st->world; ++r) {
+            volatile MailSlot* ms = &mail->slot[par][r];
+            while (ms->tag != st->run_tag + (long long)st->iter + 1) { }   // posted by rank r's k_scan of this iteration
+            __threadfence_system();
+            const double q = ms->q;
+            const unsigned long long k = ms->key;
+            if (better(q, k, bq, bk)) { bq = q; bk = k; }
+        }
+        st->selQ = bq;
+        st->sel_i = (int)(bk >> 32);
+        st->sel_j = (int)(bk & 0xffffffffu);
+    }
+    int cx, cy;
+    if (strategy) { cx = p2s[st->cx_pos]; cy = p2s[st->cy_pos]; }   // Relaxed / Random findNodes
+    else { cx = p2s[st->sel_i]; cy = p2s[st->sel_j]; }
+    if (id[cx] > id[cy]) { int t = cx; cx = cy; cy = t; }
+    st->cx = cx; st->cxn = cx < P2 ? (cx ^ 1) : -1;
+    st->cy = cy; st->cyn = cy < P2 ? (cy ^ 1) : -1;
+    st->need_rx = (st->cxn >= 0 || st->cyn >= 0);
+    if (!strategy) st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
+}
+
+// ------------------------------------------------------------------ K3b: stage the ComputeRx operands on all SMs
+// rxs[r][k*1024 + t] = w_i * D[z_r][p_i] for position i = t*L + k (segment-transposed, so the summation block reads
+// coalesced); w = 1 for the four chosen nodes and singletons, 1/2 otherwise (NetMakerOriginal.java:555-558).
+__global__ void __launch_bounds__(256)
+k_rx_stage(const double* __restrict__ D, int64_t ld, const int* __restrict__ p2s, const DevState* st, double* __restrict__ rxs,
+           int64_t rxs_ld) {
+    if (st->done || !st->need_rx) return;
+    const int m = st->m, P2 = st->P2;
+    const int Cx = st->cx, Cxn = st->cxn, Cy = st->cy, Cyn = st->cyn;
+    const int L = (m + xsum::THREADS - 1) / xsum::THREADS;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const int s = p2s[i];
+        const bool full = (s >= P2) || s == Cx || s == Cxn || s == Cy || s == Cyn;
+        const int64_t dst = (int64_t)(i % L) * xsum::THREADS + (i / L);
+        const int zs[4] = {Cx, Cxn, Cy, Cyn};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (zs[r] >= 0) {
+                const double v = D[(int64_t)zs[r] * ld + s];
+                rxs[(int64_t)r * rxs_ld + dst] = full ? v : v * 0.5;
+            }
+    }
+}
+
 // ------------------------------------------------------------------ K3: pick + bookkeeping (one block)
 constexpr int PICK_THREADS = 1024;
 
 __global__ void __launch_bounds__(PICK_THREADS, 1)
 k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState* st, int* amalg, double* trace, int serial_chain,
-       Mailbox* mail) {
+       const double* __restrict__ rxs, int64_t rxs_ld) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[4][CH_TILE] = reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw);
-    __shared__ int sh[8];
     __shared__ double rx[4];
     if (st->done) return;
     const int m = st->m, c = st->c, P2 = st->P2;
@@ -450,49 +508,16 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
         return;
     }
 
-    // ---- multi-GPU: merge the per-rank partial min-locs posted by every rank's scan
-    if (tid == 0 && st->world > 1 && !(st->mode != 0 && m > st->fallback)) {
-        const int par = st->iter & 1;
-        double bq = INFINITY;
-        unsigned long long bk = ~0ull;
-        for (int r = 0; r < st->world; ++r) {
-            volatile MailSlot* ms = &mail->slot[par][r];
-            while (ms->tag != st->run_tag + (long long)st->iter + 1) { }   // posted by rank r's k_scan of this iteration
-            __threadfence_system();
-            const double q = ms->q;
-            const unsigned long long k = ms->key;
-            if (better(q, k, bq, bk)) { bq = q; bk = k; }
-        }
-        st->selQ = bq;
-        st->sel_i = (int)(bk >> 32);
-        st->sel_j = (int)(bk & 0xffffffffu);
-    }
-    // ---- Cx, Cy from the scan key; id-order swap (:376-380)
-    if (tid == 0) {
-        int cx, cy;
-        if (st->mode != 0 && m > st->fallback) { cx = p2s[st->cx_pos]; cy = p2s[st->cy_pos]; }   // Relaxed / Random findNodes
-        else { cx = p2s[st->sel_i]; cy = p2s[st->sel_j]; }
-        if (id[cx] > id[cy]) { int t = cx; cx = cy; cy = t; }
-        sh[0] = cx; sh[1] = nbr_of(cx, P2); sh[2] = cy; sh[3] = nbr_of(cy, P2);
-        if (st->mode == 0 || m <= st->fallback)
-            st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
-    }
-    __syncthreads();
-    const int Cx = sh[0], Cxn = sh[1], Cy = sh[2], Cyn = sh[3];
+    const int Cx = st->cx, Cxn = st->cxn, Cy = st->cy, Cyn = st->cyn;   // k_select
 
     // ---- ComputeRx x<=4 (:413-420, :549-561): sequential in position order
     if (Cxn >= 0 || Cyn >= 0) {
         const int zs[4] = {Cx, Cxn, Cy, Cyn};
-        auto load = [&](int r, int i) -> double {
-            const int z = zs[r];
-            if (z < 0) return 0.0;
-            const int s = p2s[i];
-            const double v = D[(int64_t)z * ld + s];
-            const bool full = (s >= P2) || s == Cx || s == Cxn || s == Cy || s == Cyn;
-            return full ? v : v * 0.5;
-        };
-        if (serial_chain) block_seq_sum<4>(buf, m, load, rx);
-        else xsum::block_exact_seq_sum<4>(reinterpret_cast<xsum::Smem*>(smem_raw), m, load, [&](int r) { return zs[r] >= 0; }, rx);
+        const int L = (m + xsum::THREADS - 1) / xsum::THREADS;   // rxs is segment-transposed by k_rx_stage
+        auto load_seg = [&](int r, int t, int k) -> double { return rxs[(int64_t)r * rxs_ld + (int64_t)k * xsum::THREADS + t]; };
+        auto load_lin = [&](int r, int i) -> double { return zs[r] < 0 ? 0.0 : load_seg(r, i / L, i % L); };
+        if (serial_chain) block_seq_sum<4>(buf, m, load_lin, rx);
+        else xsum::block_exact_seq_sum<4>(reinterpret_cast<xsum::Smem*>(smem_raw), m, load_seg, [&](int r) { return zs[r] >= 0; }, rx);
     } else {
         if (tid < 4) rx[tid] = 0.0;
         __syncthreads();
@@ -698,6 +723,8 @@ k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevSta
           double* stage) {
     if (st->done || st->skip) return;
     const int m_new = st->m_new, P2n = st->P2_new, K = st->K, su = st->su;
+    const int Ln = (m_new + xsum::THREADS - 1) / xsum::THREADS;   // stage is segment-transposed for k_chain
+    auto sidx = [&](int p) -> int { return (p % Ln) * xsum::THREADS + p / Ln; };
     __shared__ int cslot[MAXK];
     __shared__ double cSx[MAXK];
     if (threadIdx.x < MAXK) { cslot[threadIdx.x] = st->chg_slot[threadIdx.x]; cSx[threadIdx.x] = st->chg_Sx[threadIdx.x]; }
@@ -715,8 +742,8 @@ k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevSta
         const bool pPair = t < P2n;
         if (pPair && (t & 1)) continue;
         if (t == su) {
-            stage[pos[t]] = 0.0;
-            stage[pos[t + 1]] = 0.0;
+            stage[sidx(pos[t])] = 0.0;
+            stage[sidx(pos[t + 1])] = 0.0;
             continue;
         }
         double base0 = Sx[t], base1 = pPair ? Sx[t + 1] : 0.0;
@@ -728,8 +755,8 @@ k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevSta
         if (pPair) dpu = (((r0[t] + r1[t]) + r0[t + 1]) + r1[t + 1]) * 0.25;
         else dpu = (r0[t] + r1[t]) * 0.5;
         Sx[t] = base0 + dpu;
-        stage[pos[t]] = dpu;
-        if (pPair) { Sx[t + 1] = base1 + dpu; stage[pos[t + 1]] = 0.0; }
+        stage[sidx(pos[t])] = dpu;
+        if (pPair) { Sx[t + 1] = base1 + dpu; stage[sidx(pos[t + 1])] = 0.0; }
     }
 }
 
@@ -741,9 +768,11 @@ k_chain(double* Sx, const int* id, const int* p2s, DevState* st, const double* _
     __shared__ double tot[1];
     if (st->done || st->skip) return;
     const int m_new = st->m_new;
-    auto load = [&](int, int i) -> double { return stage[i]; };
-    if (serial_chain) block_seq_sum<1>(buf, m_new, load, tot);
-    else xsum::block_exact_seq_sum<1>(reinterpret_cast<xsum::Smem*>(smem_raw), m_new, load, [](int) { return true; }, tot);
+    const int Ln = (m_new + xsum::THREADS - 1) / xsum::THREADS;
+    auto load_seg = [&](int, int t, int k) -> double { return stage[k * xsum::THREADS + t]; };
+    auto load_lin = [&](int, int i) -> double { return stage[(i % Ln) * xsum::THREADS + i / Ln]; };
+    if (serial_chain) block_seq_sum<1>(buf, m_new, load_lin, tot);
+    else xsum::block_exact_seq_sum<1>(reinterpret_cast<xsum::Smem*>(smem_raw), m_new, load_seg, [](int) { return true; }, tot);
     if (threadIdx.x == 0) {
         const int su = st->su;
         Sx[su] = tot[0];
@@ -762,9 +791,11 @@ __global__ void __launch_bounds__(PICK_THREADS, 1)
 k_seqsum(const double* __restrict__ rows, int64_t stride, int nrows, int len, double* out, int serial_chain) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ double res[4];
+    const int L = (len + xsum::THREADS - 1) / xsum::THREADS;
     auto load = [&](int r, int i) -> double { return r < nrows ? rows[(int64_t)r * stride + i] : 0.0; };
+    auto load_seg = [&](int r, int t, int k) -> double { return rows[(int64_t)r * stride + (int64_t)t * L + k]; };
     if (serial_chain) block_seq_sum<4>(reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw), len, load, res);
-    else xsum::block_exact_seq_sum<4>(reinterpret_cast<xsum::Smem*>(smem_raw), len, load, [&](int r) { return r < nrows; }, res);
+    else xsum::block_exact_seq_sum<4>(reinterpret_cast<xsum::Smem*>(smem_raw), len, load_seg, [&](int r) { return r < nrows; }, res);
     if (threadIdx.x < nrows) out[threadIdx.x] = res[threadIdx.x];
 }
 
@@ -780,6 +811,8 @@ struct fnn_ctx {
     double* Sx = nullptr;
     double* scratch = nullptr;
     double* stage = nullptr;
+    double* rxs = nullptr;            // 4 staged ComputeRx rows, segment-transposed
+    int64_t rxs_ld = 0;
     double* trace = nullptr;
     int *id = nullptr, *pos = nullptr, *p2s = nullptr, *amalg = nullptr;
     DevState* st = nullptr;
@@ -838,7 +871,7 @@ extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->o.device);
     if (c->graph) cudaGraphExecDestroy(c->graph);
-    cudaFree(c->D); cudaFree(c->Sx); cudaFree(c->scratch); cudaFree(c->stage); cudaFree(c->trace);
+    cudaFree(c->D); cudaFree(c->Sx); cudaFree(c->scratch); cudaFree(c->stage); cudaFree(c->rxs); cudaFree(c->trace);
     for (int r = 0; r < MAX_WORLD; ++r) if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
     cudaFree(c->mail); cudaFree(c->peers);
     cudaFree(c->id); cudaFree(c->pos); cudaFree(c->p2s); cudaFree(c->amalg); cudaFree(c->st); cudaFree(c->partials);
@@ -880,7 +913,9 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     FNN_ALLOC(c->D, sizeof(double) * n * c->ld);
     FNN_ALLOC(c->Sx, sizeof(double) * c->ld);
     FNN_ALLOC(c->scratch, sizeof(double) * MAXK * c->ld);
-    FNN_ALLOC(c->stage, sizeof(double) * c->ld);
+    c->rxs_ld = (int64_t)xsum::THREADS * ((n + xsum::THREADS - 1) / xsum::THREADS);
+    FNN_ALLOC(c->stage, sizeof(double) * c->rxs_ld);
+    FNN_ALLOC(c->rxs, sizeof(double) * 4 * c->rxs_ld);
     FNN_ALLOC(c->id, sizeof(int) * c->ld);
     FNN_ALLOC(c->pos, sizeof(int) * c->ld);
     FNN_ALLOC(c->p2s, sizeof(int) * c->ld);
@@ -996,8 +1031,10 @@ static int make_tensor_map(fnn_ctx* c) {
 static inline void launch_rest(fnn_ctx* c) {
     if (c->o.mode >= FNN_RANDOM_N)
         modes::k_random_select<<<1, modes::THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->p2s, c->st);
+    k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail);
+    k_rx_stage<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->p2s, c->st, c->rxs, c->rxs_ld);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
-                                                    c->serial_chain, c->mail);
+                                                    c->serial_chain, c->rxs, c->rxs_ld);
     k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
     k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage);
     k_chain<<<1, PICK_THREADS, CHAIN_SMEM, c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage, c->serial_chain);
@@ -1137,7 +1174,7 @@ static int run_relaxed(fnn_ctx* c, int64_t& launches) {
         int sel[2] = {mir.pos[Cx], mir.pos[Cy]};
         FNN_CUDA(cudaMemcpyAsync(&c->st->cx_pos, sel, sizeof(sel), cudaMemcpyHostToDevice, c->stream));
         launch_rest(c);
-        launches += 4;
+        launches += 6;
         FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
         FNN_CUDA(cudaStreamSynchronize(c->stream));
         mir.apply(c->h_st->pick_x_id, c->h_st->pick_y_id);
@@ -1228,7 +1265,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
                 ++prof_samples;
             }
             launch_rest(c);
-            launches += 5; ++scans;
+            launches += 7; ++scans;
         }
         cudaEventDestroy(p0); cudaEventDestroy(p1);
         FNN_CUDA(cudaGetLastError());
@@ -1248,7 +1285,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
             const int64_t batch = 64;  // graphs between done-flag polls
             for (int64_t b = 0; b < batch && it < max_iters; ++b, it += GI) {
                 FNN_CUDA(cudaGraphLaunch(c->graph, c->stream));
-                launches += (5 + (c->o.mode >= FNN_RANDOM_N)) * GI; scans += GI;
+                launches += (7 + (c->o.mode >= FNN_RANDOM_N)) * GI; scans += GI;
             }
             FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
             FNN_CUDA(cudaStreamSynchronize(c->stream));
@@ -1259,7 +1296,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
         while (it < max_iters) {
             for (int b = 0; b < 256 && it < max_iters; ++b, ++it) {
                 launch_scan(c); launch_rest(c);
-                launches += 5; ++scans;
+                launches += 7; ++scans;
             }
             FNN_CUDA(cudaGetLastError());
             FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
