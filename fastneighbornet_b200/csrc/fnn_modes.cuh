@@ -181,4 +181,97 @@ k_rowmin(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx
     }
 }
 
+
+// ---------------------------------------------------------------- Relaxed -additive look-ahead
+// findAgglomeratedQ (NeighborNetLocal.java:280-386) with agg3wayLocal (:388-414) / agg4wayLocal (:416-466):
+// simulate joining (Cx, Cy) and return the Q of the merged cluster against testNode, plus the Q before
+// the join (:241-245).  Cx, Cy are taken as selected (no id swap, as in the reference call at :245).
+struct LookOut { double origQ, newQ; };
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_lookahead(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ p2s,
+            const DevState* st, int cx_pos, int cy_pos, int test_pos, LookOut* out) {
+    extern __shared__ unsigned char smem_raw[];
+    xsum::Smem* xs = reinterpret_cast<xsum::Smem*>(smem_raw);
+    __shared__ double rx[4], crs[1];
+    __shared__ int sh[2];
+    const int m = st->m, c = st->c, P2 = st->P2, tid = threadIdx.x;
+    const int Cx = p2s[cx_pos], Cy = p2s[cy_pos], T = p2s[test_pos];
+    const int Cxn = Cx < P2 ? (Cx ^ 1) : -1, Cyn = Cy < P2 ? (Cy ^ 1) : -1;
+    const int L = (m + xsum::THREADS - 1) / xsum::THREADS;
+    auto d = [&](int a, int b) -> double { return D[(int64_t)a * ld + b]; };
+    const int zs[4] = {Cx, Cxn, Cy, Cyn};
+    if (Cxn >= 0 || Cyn >= 0) {
+        auto load = [&](int r, int t, int k) -> double {
+            const int s = p2s[t * L + k];
+            const double v = d(zs[r], s);
+            const bool full = (s >= P2) || s == Cx || s == Cxn || s == Cy || s == Cyn;
+            return full ? v : v * 0.5;
+        };
+        xsum::block_exact_seq_sum<4>(xs, m, load, [&](int r) { return zs[r] >= 0; }, rx);
+    } else {
+        if (tid < 4) rx[tid] = 0.0;
+        __syncthreads();
+    }
+    if (tid == 0) {   // the 4-candidate pick (:311-335)
+        int x = Cx, y = Cy;
+        const double f = (double)(c + (Cxn >= 0) + (Cyn >= 0)) - 2.0;
+        double best = (f * d(Cx, Cy) - rx[0]) - rx[2];
+        if (Cxn >= 0) { const double q = (f * d(Cxn, Cy) - rx[1]) - rx[2]; if (q < best) { x = Cxn; y = Cy; best = q; } }
+        if (Cyn >= 0) { const double q = (f * d(Cx, Cyn) - rx[0]) - rx[3]; if (q < best) { x = Cx; y = Cyn; best = q; } }
+        if (Cxn >= 0 && Cyn >= 0) { const double q = (f * d(Cxn, Cyn) - rx[1]) - rx[3]; if (q < best) { x = Cxn; y = Cyn; best = q; } }
+        sh[0] = x; sh[1] = y;
+    }
+    __syncthreads();
+    const int x = sh[0], y = sh[1];
+    const int xn = x < P2 ? (x ^ 1) : -1, yn = y < P2 ? (y ^ 1) : -1;
+    int kind, X = -1, Y = -1, Z = -1, W = -1;
+    if (xn < 0 && yn < 0) kind = 2;
+    else if (xn < 0) { kind = 3; X = x; Y = y; Z = yn; }
+    else if (yn < 0 || m == 4) { kind = 3; X = y; Y = x; Z = xn; }
+    else { kind = 4; X = xn; Y = x; Z = y; W = yn; }   // (x2, x, y, y2)
+    const double TT = 2.0 / 3.0;
+    auto term = [&](int i) -> double {   // the per-position contribution to clusterRowSum
+        const int p = p2s[i];
+        const bool pair = p < P2;
+        if (pair && (p & 1)) return 0.0;                       // not a representative
+        const int pn = pair ? p + 1 : -1;
+        if (kind == 2) {
+            if (p == x || p == y) return 0.0;
+            if (!pair) return (d(p, x) + d(p, y)) * 0.5;
+            return (((d(p, x) + d(p, y)) + d(pn, x)) + d(pn, y)) * 0.25;
+        } else if (kind == 3) {
+            if (p == X || p == Y || p == Z || pn == Y || pn == Z) return 0.0;
+            const double Dup = TT * d(X, p) + d(Y, p) / 3.0, Dvp = TT * d(Z, p) + d(Y, p) / 3.0;
+            if (!pair) return (Dup + Dvp) * 0.5;
+            const double Duq = TT * d(X, pn) + d(Y, pn) / 3.0, Dvq = TT * d(Z, pn) + d(Y, pn) / 3.0;
+            return (((Dup + Dvp) + Duq) + Dvq) * 0.25;
+        } else {
+            if (p == X || p == Y || p == Z || p == W || pn == X || pn == Y || pn == Z || pn == W) return 0.0;
+            const double Dup = TT * d(X, p) + d(Y, p) / 3.0, Dvp = TT * d(Z, p) + d(Y, p) / 3.0;
+            const double Dup2 = TT * Dup + Dvp / 3.0, Dvp2 = TT * d(W, p) + Dvp / 3.0;
+            if (!pair) return (Dup2 + Dvp2) * 0.5;
+            const double Duq = TT * d(X, pn) + d(Y, pn) / 3.0, Dvq = TT * d(Z, pn) + d(Y, pn) / 3.0;
+            const double Duq2 = TT * Duq + Dvq / 3.0, Dvq2 = TT * d(W, pn) + Dvq / 3.0;
+            return (((Dup2 + Dvp2) + Duq2) + Dvq2) * 0.25;
+        }
+    };
+    auto load1 = [&](int, int t, int k) -> double { return term(t * L + k); };
+    xsum::block_exact_seq_sum<1>(xs, m, load1, [](int) { return true; }, crs);
+    if (tid == 0) {
+        const double dCxT = dpq_roles(D, ld, Cx, T, P2), dCyT = dpq_roles(D, ld, Cy, T, P2);
+        const double subtracted = (Sx[T] - dCxT) - dCyT;                                  // :337
+        double cd;
+        if (kind == 2) {
+            const int Tn = T < P2 ? (T ^ 1) : -1;
+            // calculateClusterDistLocal(x, testNode) (:349, :468-476); a singleton testNode makes the JAR throw there -
+            // the oracle's documented substitute is the 2-term form against (x, y)
+            cd = Tn >= 0 ? (d(x, T) + d(x, Tn)) * 0.5 : (d(T, x) + d(T, y)) * 0.5;
+        } else cd = term(test_pos);
+        const double A = ((double)c - 1.0) - 2.0;
+        out->newQ = (A * cd - crs[0]) - (subtracted + cd);                                // :361 / :412 / :464
+        out->origQ = (((double)c - 2.0) * dCxT - Sx[Cx]) - Sx[T];                         // :241-243
+    }
+}
+
 }  // namespace modes

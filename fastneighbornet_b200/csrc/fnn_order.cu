@@ -886,10 +886,7 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     if (!o) { fnn_default_opts(&d); o = &d; }
     if (n > 2000000) { fnn::set_error("n too large"); return FNN_E_ARG; }
     if (o->mode < 0 || o->mode > FNN_RANDOM_LOGN) { fnn::set_error("unknown mode %d", o->mode); return FNN_E_ARG; }
-    if (o->mode == FNN_RELAXED && o->additive && n > o->canonical_fallback) {
-        fnn::set_error("-additive look-ahead (NeighborNetLocal.java:223-255) is not implemented on the device yet");
-        return FNN_E_UNSUPPORTED;
-    }
+
     int rc = ensure_device(o);
     if (rc) return rc;
     fnn_ctx* c = new fnn_ctx();
@@ -1111,6 +1108,10 @@ static int run_relaxed(fnn_ctx* c, int64_t& launches) {
     modes::RowMinOut* h_out = nullptr;
     FNN_CUDA(cudaMalloc((void**)&d_out, sizeof(modes::RowMinOut)));
     FNN_CUDA(cudaMallocHost((void**)&h_out, sizeof(modes::RowMinOut)));
+    modes::LookOut* d_look = nullptr;
+    FNN_CUDA(cudaMalloc((void**)&d_look, sizeof(modes::LookOut)));
+    FNN_CUDA(cudaFuncSetAttribute(modes::k_lookahead, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(xsum::Smem)));
+    const bool additive = c->o.additive != 0;
     int rc = FNN_OK;
     int Cx = 0, Cy = 0;   // node ids; persist across iterations like the Java fields
     std::vector<std::vector<RowMinHost>> lists;
@@ -1165,7 +1166,26 @@ static int run_relaxed(fnn_ctx* c, int64_t& launches) {
             if (!myMinimums.empty()) {
                 const RowMinHost pick = myMinimums[rng.nextInt((int)myMinimums.size())];
                 Cx = pick.me; Cy = pick.row;
-                chosen = true;   // non-additive: break outerloop (:257)
+                if (!additive) { chosen = true; continue; }   // break outerloop (:257)
+                // -additive (:223-255): accept the join only if it leaves Q against a third cluster unchanged.  The
+                // reference repeats the identical test myMinimums.size() times (Cx, Cy are not re-read, :250-254), so one
+                // evaluation decides.  testNode: last active node outside both clusters (intended loop).
+                int testNode = 0;
+                for (int j = mir.m - 1; j >= 0; --j) {
+                    const int t = mir.act[j];
+                    if (t == Cx || t == Cy || t == mir.nbr[Cx] || t == mir.nbr[Cy]) continue;
+                    testNode = t;
+                    break;
+                }
+                if (testNode == 0) { chosen = true; continue; }
+                if (mir.nbr[testNode] && mir.nbr[testNode] < testNode) testNode = mir.nbr[testNode];
+                modes::k_lookahead<<<1, modes::THREADS, sizeof(xsum::Smem), c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, mir.pos[Cx],
+                                                                                        mir.pos[Cy], mir.pos[testNode], d_look);
+                ++launches;
+                modes::LookOut lk;
+                if (cudaMemcpyAsync(&lk, d_look, sizeof(lk), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = FNN_E_CUDA; break; }
+                if (std::fabs(lk.origQ - lk.newQ) < .0000001) chosen = true;
             }
         }
         if (rc) break;
@@ -1182,6 +1202,7 @@ static int run_relaxed(fnn_ctx* c, int64_t& launches) {
     }
     if (rc == FNN_E_UNSUPPORTED) fnn::set_error("relaxed row scan: more than %d exact ties in one row", modes::MAX_TIES);
     cudaFree(d_out);
+    cudaFree(d_look);
     cudaFreeHost(h_out);
     return rc;
 }

@@ -412,11 +412,13 @@ struct Engine {
                 RowMin c = myMinimums[choice];
                 Cx = c.me; Cy = c.row;
                 if (additive) {
-                    int initial = choice;
-                    int mx = (int)myMinimums.size();
+                    // The reference loops `choice = (choice+1) % max` until it is back at `initial` (:226-255), but it
+                    // never re-reads combineMe, so every pass repeats the IDENTICAL test on the same (Cx, Cy): the
+                    // outcome of the first pass is the outcome of the loop.  Evaluate once (the literal loop costs
+                    // myMinimums.size() identical O(m) look-aheads and myMinimums is never cleared, :172).
                     bool accepted = false;
-                    while (true) {
-                        // INTENDED loop (documented deviation): the shipped
+                    {
+                        // INTENDED test-node loop (documented deviation): the shipped
                         // `for (int j = num_active-1; i > 0; i--)` never moves j and NPEs when
                         // netNodes[num_active-1] lies in the two clusters.
                         int testNode = -1;
@@ -427,17 +429,14 @@ struct Engine {
                             if (t == Cx || t == Cy || t == nd[Cx].nbr || t == nd[Cy].nbr) continue;
                             testNode = t; break;
                         }
-                        if (testNode < 0) { accepted = true; break; }   // nothing outside the two clusters
-                        if (nd[testNode].nbr >= 0 && nd[nd[testNode].nbr].id < nd[testNode].id) testNode = nd[testNode].nbr;
-                        double originalDistCx = clusterDist(Cx, testNode);
-                        double originalQ = ((double)num_clusters - 2.0) * originalDistCx - nd[Cx].Sx - nd[testNode].Sx;
-                        double newQ = findAgglomeratedQ(Cx, Cy, testNode, num_clusters, num_active);
-                        if (std::fabs(originalQ - newQ) < .0000001) { accepted = true; break; }
-                        choice++;
-                        choice %= mx;
-                        if (choice == initial) break;
-                        // NB (literal): the reference does not re-read combineMe here, so Cx/Cy stay
-                        // those of the first choice; `choice` only counts attempts.
+                        if (testNode < 0) accepted = true;   // nothing outside the two clusters
+                        else {
+                            if (nd[testNode].nbr >= 0 && nd[nd[testNode].nbr].id < nd[testNode].id) testNode = nd[testNode].nbr;
+                            double originalDistCx = clusterDist(Cx, testNode);
+                            double originalQ = ((double)num_clusters - 2.0) * originalDistCx - nd[Cx].Sx - nd[testNode].Sx;
+                            double newQ = findAgglomeratedQ(Cx, Cy, testNode, num_clusters, num_active);
+                            if (std::fabs(originalQ - newQ) < .0000001) accepted = true;
+                        }
                     }
                     if (accepted) return;
                 } else {

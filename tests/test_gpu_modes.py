@@ -55,3 +55,19 @@ def test_reference_style_classes_modes(fnn):
     assert (fnn.NeighborNetLocal(D, 1200, 1, False, None).runNeighborNet() == o_ref).all()
     o_ref, _, _ = oracle.order(D, mode="random_logn", seed=12345, mult=3)
     assert (fnn.NeighborNetRandom(D, 1200, 1, None, "LOGN", 3).runNeighborNet() == o_ref).all()
+
+
+@pytest.mark.parametrize("n,fallback,eps_list", [(40, 8, (0.0, 0.05)), (120, 8, (0.0, 0.05)), (1100, 1024, (0.0,))])
+def test_relaxed_additive_lookahead(fnn, n, fallback, eps_list):
+    """-additive (NeighborNetLocal.java:223-255, findAgglomeratedQ :280-466) with the intended test-node loop.
+    On non-additive data nearly every check fails and the reference degenerates to one look-ahead per sampled row
+    (O(m) look-aheads per iteration), so the noisy cases are kept small."""
+    for eps in eps_list:
+        D = tree_matrix(n, 1, eps)
+        o_ref, tr_ref, _ = oracle.order(D, mode="relaxed", seed=32, fallback=fallback, additive=True)
+        with fnn.Context(n, record_trace=1, mode="relaxed", seed=32, canonical_fallback=fallback, additive=1) as c:
+            c.load_host(D)
+            o = c.order()
+            tr = c.trace()
+        assert tr.shape == tr_ref.shape and (tr == tr_ref).all()
+        assert (o == o_ref).all()
