@@ -285,7 +285,9 @@ def main():
                     "traffic": None, "peak_source": peak_src, "samples": ps["prof_scan_samples"],
                     "avg_launch_ms": ps["prof_scan_ms"] / max(1, ps["prof_scan_samples"]),
                     "alg_bytes_per_launch": ps["prof_scan_bytes"] / max(1, ps["prof_scan_samples"]),
-                    "scan_share_of_step": (ps["prof_scan_ms"] * 16) / (1e3 * elapsed / args.steps)}
+                    "scan_share_of_step": ((ps["prof_scan_ms"] * 16) / (1e3 * elapsed / args.steps)) if world == 1 else None}
+        if world > 1:
+            roofline["note"] = "kernel profiled on rank 0 as a single-GPU run of the same workload (each rank launches it on 1/world of the tiles)"
         tfile = os.path.join(ROOT, "profiles", "scan_traffic.json")
         if os.path.exists(tfile):
             try:

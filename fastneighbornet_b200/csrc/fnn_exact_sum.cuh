@@ -30,6 +30,8 @@ namespace xsum {
 
 constexpr int THREADS = 1024;
 constexpr int LEAF_MAX = 128;        // max segment length (chains up to 131072 elements)
+constexpr int PROLOGUE = 512;        // the first ~512 elements hold most binade crossings: summed sequentially up front
+constexpr int LEAF_BUF = PROLOGUE + LEAF_MAX;
 constexpr double TWO53 = 9007199254740992.0;
 constexpr unsigned long long M52 = (1ull << 52) - 1;
 constexpr int E_INVALID = 0, E_IDENT = -1;   // summary exponent codes (else: biased exponent 1..2046)
@@ -40,7 +42,7 @@ struct Smem {
     int wE[4][32];
     double cC[4][THREADS];
     int cE[4][THREADS];
-    double leaf[4][LEAF_MAX];
+    double leaf[4][LEAF_BUF];
     double result[4];
 };
 
@@ -192,37 +194,41 @@ __device__ void block_exact_seq_sum(Smem* sm, int len, Loader load, Present pres
         if (present(r)) {
             const int we = sm->wE[r][lane];
             const double wc = sm->wC[r][lane];
-            int s2 = 0;
-            while (s2 < 32) {
-                s2 = coop_apply(s, we, wc, s2, lane);
-#ifdef FNN_XSUM_TIMING
-                ++ncoop_;
-#endif
-                if (s2 >= 32) break;
-                const int w = s2;                              // warp summary w is not applicable: open it
+            // sequential adds of elements [j0, j1) staged through shared memory (s stays uniform across the warp)
+            auto leaf_sum = [&](int j0, int j1) {
+                for (int k = lane; k < j1 - j0; k += 32) sm->leaf[r][k] = load(r, (j0 + k) / L, (j0 + k) % L);
+                __syncwarp();
+                const double* e = sm->leaf[r];
+                int k = 0;
+                for (; k + 4 <= j1 - j0; k += 4) {
+                    const double v0 = e[k], v1 = e[k + 1], v2 = e[k + 2], v3 = e[k + 3];
+                    s += v0; s += v1; s += v2; s += v3;
+                }
+                for (; k < j1 - j0; ++k) s += e[k];
+                __syncwarp();
+            };
+            // open warp summary w from its segment s1: cooperative prefixes, sequential leaves
+            auto open_warp = [&](int w, int s1) {
                 const int te = sm->cE[r][w * 32 + lane];
                 const double tc = sm->cC[r][w * 32 + lane];
-                int s1 = 0;
                 while (s1 < 32) {
                     s1 = coop_apply(s, te, tc, s1, lane);
-#ifdef FNN_XSUM_TIMING
-                    ++ncoop_; if (s1 < 32) ++nleaf_;
-#endif
                     if (s1 >= 32) break;
-                    const int t = w * 32 + s1;                 // segment t is not applicable: plain sequential adds
-                    const int j0 = min(t * L, len), j1 = min(j0 + L, len);
-                    for (int k = lane; k < j1 - j0; k += 32) sm->leaf[r][k] = load(r, t, k);
-                    __syncwarp();
-                    const double* e = sm->leaf[r];
-                    int k = 0;
-                    for (; k + 4 <= j1 - j0; k += 4) {
-                        const double v0 = e[k], v1 = e[k + 1], v2 = e[k + 2], v3 = e[k + 3];
-                        s += v0; s += v1; s += v2; s += v3;
-                    }
-                    for (; k < j1 - j0; ++k) s += e[k];
-                    __syncwarp();
+                    const int t = w * 32 + s1;
+                    leaf_sum(min(t * L, len), min(t * L + L, len));
                     s1 += 1;
                 }
+            };
+            // prologue: the running sum doubles every few elements at the start (binade crossings at ~2^j / mean),
+            // so the first segments are never collapsible - add them sequentially in one go
+            const int S0 = min(32, (PROLOGUE + L - 1) / L);
+            leaf_sum(0, min(S0 * L, len));
+            open_warp(0, S0);
+            int s2 = 1;
+            while (s2 < 32) {
+                s2 = coop_apply(s, we, wc, s2, lane);
+                if (s2 >= 32) break;
+                open_warp(s2, 0);
                 s2 += 1;
             }
         }

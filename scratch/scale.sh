@@ -1,0 +1,7 @@
+N=$1
+if [ "$N" = "1" ]; then
+  python bench.py --gpus 1 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/scale_$N.json 2> gpurun_out/scale_$N.err
+else
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29540 bench.py --gpus $N --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/scale_$N.json 2> gpurun_out/scale_$N.err
+fi
+echo "rc=$?"; tail -c 1500 gpurun_out/scale_$N.json; tail -3 gpurun_out/scale_$N.err | cut -c1-300
