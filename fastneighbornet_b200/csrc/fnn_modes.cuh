@@ -51,77 +51,241 @@ __device__ __forceinline__ int ceil_log10(int total) {
 }
 
 // ---------------------------------------------------------------- Random findNodes
-__global__ void __launch_bounds__(THREADS, 1)
-k_random_select(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ pos,
-                const int* __restrict__ p2s, DevState* st) {
-    if (st->done || st->mode < 2 || st->m <= st->fallback) return;
-    __shared__ int si[THREADS], sj[THREADS];
-    __shared__ int scount;
-    __shared__ double wq[THREADS / 32];
-    __shared__ unsigned long long wk[THREADS / 32];
-    __shared__ int wi[THREADS / 32], wj[THREADS / 32];
-    const int m = st->m, P2 = st->P2, tid = threadIdx.x;
-    const double cm2 = (double)st->c - 2.0;
-    long long amount;   // findSearchAmount (:31-48)
-    if (st->mode == 4) amount = ceil_log10(m);
-    else if (st->mode == 2) amount = m;
-    else amount = (long long)ceil_log10(m) * m;
-    const long long searchAmount = (long long)st->mult * amount;
+// The walk of NeighborNetRandom.java:140-158 is a chain: draw k uses bound m-1 or m-2 depending on whether the
+// node reached by draw k-1 is paired, nextInt(bound) may reject (consuming more LCG steps), and j is remapped when
+// it hits i or i.nbr.  k_random_walk still generates it in PARALLEL, by speculation:
+//   * raw 31-bit values for a window of draws by LCG jump-ahead (one LCG step per draw if nothing rejects);
+//   * both candidates (mod m-1, mod m-2) per draw; "is the reached node paired" is a 2-state automaton whose
+//     per-draw transition functions are composed with a block-wide scan;
+//   * rejections and remaps are rare (~bound/2^31 and ~2/m per draw): the first one in the window is found with
+//     a min-reduce, everything before it is committed, that single draw is replayed exactly by one lane, and the
+//     window restarts behind it.
+// The committed (i, j) pairs go to global memory; k_random_eval evaluates Q for them on all SMs and reduces on
+// (Q, draw index) = "first strict minimum in draw order" (:172-176).
+constexpr unsigned long long JR_A = 0x5DEECE66DULL, JR_C = 0xBULL, JR_MASK = (1ULL << 48) - 1;
+constexpr int WALK_G = 8;                       // draws per thread per window
+constexpr int WALK_W = THREADS * WALK_G;        // window
 
-    unsigned long long rng = st->rng;
-    int cur = 0;
-    if (tid == 0) cur = jr_next_int(rng, m);
-    double bq = 0.0;
-    unsigned long long bk = ~0ull;
-    int bi = -1, bj = -1;
-    for (long long base = 0; base < searchAmount; base += THREADS) {
+// first-try result of java.util.Random.nextInt(bound) for the raw 31-bit value u
+__device__ __forceinline__ int jr_cand(int u, int bound) {
+    return (bound & (bound - 1)) == 0 ? (int)(((long long)bound * (long long)u) >> 31) : u % bound;
+}
+
+struct WalkState { long long count; long long total; int cur; int pad; };
+
+// state after k LCG steps: s -> A^k s + C (A^k - 1)/(A - 1)   (mod 2^48), by binary decomposition of k
+__device__ __forceinline__ unsigned long long jr_jump(unsigned long long s, unsigned k, const unsigned long long* Ap,
+                                                      const unsigned long long* Cp) {
+    for (int b = 0; k; ++b, k >>= 1)
+        if (k & 1) s = (Ap[b] * s + Cp[b]) & JR_MASK;
+    return s;
+}
+
+__device__ __forceinline__ long long random_search_amount(int mode, int mult, int m) {   // findSearchAmount (:31-48)
+    long long amount;
+    if (mode == 4) amount = ceil_log10(m);
+    else if (mode == 2) amount = m;
+    else amount = (long long)ceil_log10(m) * m;
+    return (long long)mult * amount;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_random_walk(const int* __restrict__ pos, const int* __restrict__ p2s, DevState* st, int* __restrict__ nbrpos,
+              int2* __restrict__ pairs, WalkState* ws) {
+    if (st->done || st->mode < 2 || st->m <= st->fallback) return;
+    __shared__ unsigned long long Ap[24], Cp[24];
+    __shared__ unsigned char wfun[THREADS / 32];
+    __shared__ int wlast[THREADS / 32];
+    __shared__ int wexc[THREADS / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ int s_cur, s_exc;
+    __shared__ long long s_count;
+    const int m = st->m, P2 = st->P2, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long total = random_search_amount(st->mode, st->mult, m);
+    // neighbour position per position (-1: singleton), shared by this kernel's parallel lookups
+    for (int i = tid; i < m; i += THREADS) {
+        const int s = p2s[i];
+        nbrpos[i] = s < P2 ? pos[s ^ 1] : -1;
+    }
+    if (tid == 0) {
+        unsigned long long a = JR_A, c = JR_C;
+        for (int b = 0; b < 24; ++b) { Ap[b] = a; Cp[b] = c; c = (c * (a + 1)) & JR_MASK; a = (a * a) & JR_MASK; }
+        unsigned long long rng = st->rng;
+        s_cur = jr_next_int(rng, m);   // int i = myRandom.nextInt(num_active) (:134)
+        s_base = rng;
+        s_count = 0;
+    }
+    __syncthreads();   // also publishes nbrpos (block-local producer/consumer through global memory)
+    __threadfence_block();
+    while (true) {
+        const long long count = s_count;
+        if (count >= total) break;
+        const unsigned long long base = s_base;
+        const int cur0 = s_cur;
+        const int wlen = (int)min((long long)WALK_W, total - count);
+        const int d0 = tid * WALK_G;
+        // ---- raw values + both candidates of my draws
+        int ra[WALK_G], ca[WALK_G], cb[WALK_G];
+        unsigned long long sst = (d0 < wlen) ? jr_jump(base, (unsigned)d0, Ap, Cp) : 0ull;
+        unsigned f0 = 0, f1 = 1;   // composed transition so far: state in -> state out
+#pragma unroll
+        for (int g = 0; g < WALK_G; ++g) {
+            if (d0 + g < wlen) {
+                sst = (sst * JR_A + JR_C) & JR_MASK;
+                const int u = (int)(sst >> 17);
+                ra[g] = u;
+                ca[g] = jr_cand(u, m - 1);   // candidate when the current node is a singleton
+                cb[g] = jr_cand(u, m - 2);   // candidate when it is paired
+                const unsigned pa = nbrpos[ca[g]] >= 0, pb = nbrpos[cb[g]] >= 0;
+                // compose: new f(x) = (old f(x) ? pb : pa)
+                f0 = f0 ? pb : pa;
+                f1 = f1 ? pb : pa;
+            }
+        }
+        // ---- block-wide composition scan of the 2-state transition functions (exclusive)
+        unsigned c0 = f0, c1 = f1;   // inclusive composition within the warp
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned p0 = __shfl_up_sync(0xffffffffu, c0, off), p1 = __shfl_up_sync(0xffffffffu, c1, off);
+            if (lane >= off) { const unsigned n0 = p0 ? c1 : c0, n1 = p1 ? c1 : c0; c0 = n0; c1 = n1; }   // (prev then mine)
+        }
+        if (lane == 31) wfun[warp] = (unsigned char)(c0 | (c1 << 1));
+        __syncthreads();
+        // incoming state of this thread = composition of everything before it applied to the start state
+        unsigned st_in = nbrpos[cur0] >= 0;
+        for (int w = 0; w < warp; ++w) st_in = (wfun[w] >> st_in) & 1u;
+        {
+            const unsigned e0 = __shfl_up_sync(0xffffffffu, c0, 1), e1 = __shfl_up_sync(0xffffffffu, c1, 1);
+            if (lane > 0) st_in = st_in ? e1 : e0;
+        }
+        // ---- replay my draws: chosen candidate, exceptions
+        int jj[WALK_G];
+        int myexc = 0x7fffffff, mylast = -1;
+        unsigned sx = st_in;
+#pragma unroll
+        for (int g = 0; g < WALK_G; ++g) {
+            if (d0 + g < wlen) {
+                const int bound = sx ? (m - 2) : (m - 1);
+                const int j = sx ? cb[g] : ca[g];
+                jj[g] = j;
+                if ((bound & (bound - 1)) != 0 && (int)((unsigned)ra[g] - (unsigned)j + (unsigned)(bound - 1)) < 0)
+                    myexc = min(myexc, d0 + g);   // nextInt would reject and draw again
+                sx = nbrpos[j] >= 0;
+                mylast = j;
+            }
+        }
+        if (lane == 31 || d0 + WALK_G >= wlen) { /* last j of the warp is published below */ }
+        // previous draw's j (= my first i): from the previous thread, or cur0
+        int prevj = __shfl_up_sync(0xffffffffu, mylast, 1);
+        if (lane == 31) wlast[warp] = mylast;
+        __syncthreads();
+        if (lane == 0) prevj = (warp == 0) ? cur0 : wlast[warp - 1];
+        int ii = prevj;
+#pragma unroll
+        for (int g = 0; g < WALK_G; ++g) {
+            if (d0 + g < wlen) {
+                const int inb = nbrpos[ii];
+                if (jj[g] == ii || (inb >= 0 && jj[g] == inb)) myexc = min(myexc, d0 + g);   // remap cases (:144-157)
+                ii = jj[g];
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) myexc = min(myexc, __shfl_xor_sync(0xffffffffu, myexc, off));
+        if (lane == 0) wexc[warp] = myexc;
+        __syncthreads();
         if (tid == 0) {
-            const int cnt = (int)min((long long)THREADS, searchAmount - base);
-            for (int k = 0; k < cnt; ++k) {   // the walk of :140-158
-                const int i = cur;
-                const int s = p2s[i];
+            int e = wexc[0];
+            for (int w = 1; w < THREADS / 32; ++w) e = min(e, wexc[w]);
+            s_exc = e;
+        }
+        __syncthreads();
+        const int exc = min(s_exc, wlen);   // draws [0, exc) are exactly the reference's
+        // ---- commit
+        ii = prevj;
+#pragma unroll
+        for (int g = 0; g < WALK_G; ++g) {
+            if (d0 + g < exc) pairs[count + d0 + g] = make_int2(ii, jj[g]);
+            if (d0 + g < wlen) ii = jj[g];
+        }
+        // new walk position = j of draw exc-1
+        if (exc > 0 && d0 <= exc - 1 && exc - 1 < d0 + WALK_G) s_cur = jj[exc - 1 - d0];
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long rng = jr_jump(base, (unsigned)exc, Ap, Cp);
+            long long done_n = exc;
+            if (exc < wlen) {   // replay the exceptional draw exactly
+                const int i = s_cur;
+                const int inb = nbrpos[i];
                 int j;
-                if (s < P2) {
-                    const int iNbr = pos[s ^ 1];
+                if (inb >= 0) {
                     j = jr_next_int(rng, m - 2);
-                    if (i == j && m - 1 == iNbr) j = m - 2;
-                    else if (i == j && m - 1 != iNbr) j = m - 1;
-                    else if (iNbr == j && m - 2 == i) j = m - 1;
-                    else if (iNbr == j && m - 2 != i) j = m - 2;
+                    if (i == j && m - 1 == inb) j = m - 2;
+                    else if (i == j && m - 1 != inb) j = m - 1;
+                    else if (inb == j && m - 2 == i) j = m - 1;
+                    else if (inb == j && m - 2 != i) j = m - 2;
                 } else {
                     j = jr_next_int(rng, m - 1);
                     if (i == j) j = m - 1;
                 }
-                si[k] = i; sj[k] = j;
-                cur = j;
+                pairs[count + exc] = make_int2(i, j);
+                s_cur = j;
+                done_n += 1;
             }
-            scount = cnt;
-        }
-        __syncthreads();
-        if (tid < scount) {
-            const int i = si[tid], j = sj[tid];
-            const int sp = p2s[i], sq = p2s[j];
-            const double q = (cm2 * dpq_roles(D, ld, sp, sq, P2) - Sx[sp]) - Sx[sq];
-            const unsigned long long key = (unsigned long long)(base + tid);
-            if (bi < 0 || q < bq || (q == bq && key < bk)) { bq = q; bk = key; bi = i; bj = j; }
+            s_base = rng;
+            s_count = count + done_n;
         }
         __syncthreads();
     }
-    // block reduce on (Q, draw index); invalid lanes carry bi < 0
+    if (tid == 0) {
+        st->rng = s_base;
+        ws->count = s_count;
+        ws->total = total;
+    }
+}
+
+// Q for every committed pair, min-loc on (Q, draw index); the last block reduces the partials
+__global__ void __launch_bounds__(256)
+k_random_eval(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ p2s,
+              DevState* st, const int2* __restrict__ pairs, const WalkState* ws, Partial* partials, unsigned int* ticket) {
+    if (st->done || st->mode < 2 || st->m <= st->fallback) return;
+    __shared__ double wq[8];
+    __shared__ unsigned long long wk[8];
+    __shared__ bool amLast;
+    const int P2 = st->P2, tid = threadIdx.x;
+    const double cm2 = (double)st->c - 2.0;
+    const long long total = ws->count;
+    double bq = INFINITY;
+    unsigned long long bk = ~0ull;
+    for (long long k = (long long)blockIdx.x * blockDim.x + tid; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int2 pr = pairs[k];
+        const int sp = p2s[pr.x], sq = p2s[pr.y];
+        const double q = (cm2 * dpq_roles(D, ld, sp, sq, P2) - Sx[sp]) - Sx[sq];
+        if (bk == ~0ull || q < bq || (q == bq && (unsigned long long)k < bk)) { bq = q; bk = (unsigned long long)k; }
+    }
+    auto take = [&](double oq, unsigned long long ok) {
+        if (ok != ~0ull && (bk == ~0ull || oq < bq || (oq == bq && ok < bk))) { bq = oq; bk = ok; }
+    };
     for (int off = 16; off > 0; off >>= 1) {
         const double oq = __shfl_down_sync(0xffffffffu, bq, off);
         const unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, off);
-        const int oi = __shfl_down_sync(0xffffffffu, bi, off), oj = __shfl_down_sync(0xffffffffu, bj, off);
-        if (oi >= 0 && (bi < 0 || oq < bq || (oq == bq && ok < bk))) { bq = oq; bk = ok; bi = oi; bj = oj; }
+        take(oq, ok);
     }
-    if ((tid & 31) == 0) { wq[tid >> 5] = bq; wk[tid >> 5] = bk; wi[tid >> 5] = bi; wj[tid >> 5] = bj; }
+    if ((tid & 31) == 0) { wq[tid >> 5] = bq; wk[tid >> 5] = bk; }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < THREADS / 32; ++w)
-            if (wi[w] >= 0 && (bi < 0 || wq[w] < bq || (wq[w] == bq && wk[w] < bk))) { bq = wq[w]; bk = wk[w]; bi = wi[w]; bj = wj[w]; }
-        st->cx_pos = bi;   // Cx = p, Cy = q (:173-176)
-        st->cy_pos = bj;
-        st->rng = rng;
+        for (int w = 1; w < 8; ++w) take(wq[w], wk[w]);
+        partials[blockIdx.x] = Partial{bq, bk};
+        __threadfence();
+        amLast = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (amLast && tid == 0) {
+        __threadfence();
+        bq = INFINITY; bk = ~0ull;
+        for (int b = 0; b < (int)gridDim.x; ++b) take(__ldcg(&partials[b].q), __ldcg(&partials[b].key));
+        const int2 pr = pairs[bk];
+        st->cx_pos = pr.x;   // Cx = p, Cy = q (:173-176)
+        st->cy_pos = pr.y;
+        *ticket = 0;
     }
 }
 

@@ -812,6 +812,10 @@ struct fnn_ctx {
     double* scratch = nullptr;
     double* stage = nullptr;
     double* rxs = nullptr;            // 4 staged ComputeRx rows, segment-transposed
+    int* nbrpos = nullptr;            // Random modes: neighbour position per position, the walk's (i, j) pairs
+    int2* pairs = nullptr;
+    modes::WalkState* walk = nullptr;
+    unsigned int* walk_ticket = nullptr;
     int64_t rxs_ld = 0;
     double* trace = nullptr;
     int *id = nullptr, *pos = nullptr, *p2s = nullptr, *amalg = nullptr;
@@ -874,6 +878,7 @@ extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
     cudaFree(c->D); cudaFree(c->Sx); cudaFree(c->scratch); cudaFree(c->stage); cudaFree(c->rxs); cudaFree(c->trace);
     for (int r = 0; r < MAX_WORLD; ++r) if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
     cudaFree(c->mail); cudaFree(c->peers);
+    cudaFree(c->nbrpos); cudaFree(c->pairs); cudaFree(c->walk); cudaFree(c->walk_ticket);
     cudaFree(c->id); cudaFree(c->pos); cudaFree(c->p2s); cudaFree(c->amalg); cudaFree(c->st); cudaFree(c->partials);
     if (c->h_st) cudaFreeHost(c->h_st);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -931,6 +936,17 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     c->row_grid = std::max<int>(1, std::min<int64_t>((n + 255) / 256, c->sms * 4));
     FNN_ALLOC(c->partials, sizeof(Partial) * c->scan_grid);
     if (o->record_trace) FNN_ALLOC(c->trace, sizeof(double) * 8 * (n + 8));
+    if (o->mode >= FNN_RANDOM_N) {
+        int lg = 0;
+        for (long long p10 = 1; p10 < n; p10 *= 10) ++lg;
+        const long long amount = o->mode == FNN_RANDOM_LOGN ? lg : (o->mode == FNN_RANDOM_N ? n : (long long)lg * n);
+        const long long max_pairs = std::max<long long>(1, (long long)o->mult * amount) + 8;
+        FNN_ALLOC(c->nbrpos, sizeof(int) * c->ld);
+        FNN_ALLOC(c->pairs, sizeof(int2) * max_pairs);
+        FNN_ALLOC(c->walk, sizeof(modes::WalkState));
+        FNN_ALLOC(c->walk_ticket, sizeof(unsigned int));
+        FNN_CUDA(cudaMemset(c->walk_ticket, 0, sizeof(unsigned int)));
+    }
     FNN_CUDA(cudaMallocHost((void**)&c->h_st, sizeof(DevState)));
     FNN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     FNN_CUDA(cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICK_SMEM));
@@ -1026,8 +1042,11 @@ static int make_tensor_map(fnn_ctx* c) {
     return FNN_OK;
 }
 static inline void launch_rest(fnn_ctx* c) {
-    if (c->o.mode >= FNN_RANDOM_N)
-        modes::k_random_select<<<1, modes::THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->p2s, c->st);
+    if (c->o.mode >= FNN_RANDOM_N) {
+        modes::k_random_walk<<<1, modes::THREADS, 0, c->stream>>>(c->pos, c->p2s, c->st, c->nbrpos, c->pairs, c->walk);
+        modes::k_random_eval<<<c->sms * 2, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, c->pairs, c->walk, c->partials,
+                                                                c->walk_ticket);
+    }
     k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail);
     k_rx_stage<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->p2s, c->st, c->rxs, c->rxs_ld);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
@@ -1306,7 +1325,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
             const int64_t batch = 64;  // graphs between done-flag polls
             for (int64_t b = 0; b < batch && it < max_iters; ++b, it += GI) {
                 FNN_CUDA(cudaGraphLaunch(c->graph, c->stream));
-                launches += (7 + (c->o.mode >= FNN_RANDOM_N)) * GI; scans += GI;
+                launches += (7 + 2 * (c->o.mode >= FNN_RANDOM_N)) * GI; scans += GI;
             }
             FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
             FNN_CUDA(cudaStreamSynchronize(c->stream));

@@ -71,3 +71,9 @@ def test_relaxed_additive_lookahead(fnn, n, fallback, eps_list):
             tr = c.trace()
         assert tr.shape == tr_ref.shape and (tr == tr_ref).all()
         assert (o == o_ref).all()
+
+
+def test_random_n3000_exercises_rejections(fnn):
+    """~3e7 draws: dozens of nextInt rejections and hundreds of i/i.nbr remaps must be replayed exactly by the
+    speculative parallel walk (k_random_walk)."""
+    _check(fnn, tree_matrix(3000, 6, 0.05), "random_n", seed=2024, fallback=1024)
