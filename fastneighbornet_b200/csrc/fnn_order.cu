@@ -81,7 +81,15 @@ struct Partial { double q; unsigned long long key; };
 // (Q, i, j) min-loc into slot [iteration parity][rank] of EVERY peer's mailbox with plain stores over
 // NVLink (peer memory mapped through CUDA IPC); the tag carries the iteration number.
 constexpr int MAX_WORLD = 8;
-struct MailSlot { double q; unsigned long long key; long long tag; long long pad; };
+// two 16-byte halves, each written with ONE vector store and carrying the tag, so no fence is needed between the
+// payload and the tag: a half is either entirely old or entirely new
+struct __align__(16) MailSlot { double q; long long tag0; unsigned long long key; long long tag1; };
+__device__ __forceinline__ void mail_store(void* p, unsigned long long a, long long b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void mail_load(const void* p, unsigned long long& a, long long& b) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 struct Mailbox { MailSlot slot[2][MAX_WORLD]; };
 struct PeerTable { Mailbox* box[MAX_WORLD]; };
 
@@ -420,11 +428,12 @@ __global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s
         double bq = INFINITY;
         unsigned long long bk = ~0ull;
         for (int r = 0; r < st->world; ++r) {
-            volatile MailSlot* ms = &mail->slot[par][r];
-            while (ms->tag != st->run_tag + (long long)st->iter + 1) { }   // posted by rank r's k_scan of this iteration
-            __threadfence_system();
-            const double q = ms->q;
-            const unsigned long long k = ms->key;
+            const MailSlot* ms = &mail->slot[par][r];
+            const long long want = st->run_tag + (long long)st->iter + 1;   // posted by rank r's k_scan of this iteration
+            unsigned long long qb, k;
+            long long t0, t1;
+            do { mail_load(&ms->q, qb, t0); mail_load(&ms->key, k, t1); } while (t0 != want || t1 != want);
+            const double q = __longlong_as_double((long long)qb);
             if (better(q, k, bq, bk)) { bq = q; bk = k; }
         }
         st->selQ = bq;

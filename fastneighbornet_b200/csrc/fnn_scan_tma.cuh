@@ -381,17 +381,13 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
                 if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
             st->ticket = 0;
             if (st->world > 1) {
-                // post this rank's partial into every rank's mailbox (own included); k_pick merges
+                // post this rank's partial into every rank's mailbox (own included); k_select merges
                 const int par = st->iter & 1;
+                const long long tag = st->run_tag + (long long)st->iter + 1;
                 for (int r = 0; r < st->world; ++r) {
-                    volatile MailSlot* ms = &peers->box[r]->slot[par][st->rank];
-                    ms->q = bq;
-                    ms->key = bk;
-                }
-                __threadfence_system();
-                for (int r = 0; r < st->world; ++r) {
-                    volatile MailSlot* ms = &peers->box[r]->slot[par][st->rank];
-                    ms->tag = st->run_tag + (long long)st->iter + 1;
+                    MailSlot* ms = &peers->box[r]->slot[par][st->rank];
+                    mail_store(&ms->q, (unsigned long long)__double_as_longlong(bq), tag);
+                    mail_store(&ms->key, bk, tag);
                 }
                 __threadfence_system();
             } else {
