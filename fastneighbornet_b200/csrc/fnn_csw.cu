@@ -66,29 +66,73 @@ __global__ void k_rowscan(const double* __restrict__ v, double* __restrict__ Rw,
 }
 
 // ---------------------------------------------------------------- prefix2d: column pass (+ raw column sums)
+// Blocked like the row pass: chunks of 32 rows are scanned top to bottom from zero (k_colscan_local), the chunk
+// totals are accumulated sequentially per column (k_colscan_carry), and the carry is added to every entry
+// (k_colscan_fix): P(i,j) = carry(chunk(i), j) + local(i, j).  Parallelism n * n/32 instead of n.
+constexpr int COL_CHUNK = 32;
+
 template <bool WITH_CT>
-__global__ void k_colscan(const double* __restrict__ Rw, const double* __restrict__ v, double* __restrict__ P,
-                          double* __restrict__ CT, int n, const int* done) {
+__global__ void k_colscan_local(const double* __restrict__ Rw, const double* __restrict__ v, double* __restrict__ P,
+                                double* __restrict__ T, double* __restrict__ T2, int n, const int* done) {
+    if (done && *done) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (j >= n) return;
+    const int i0 = c * COL_CHUNK, i1 = min(i0 + COL_CHUNK, j);   // rows i < j
+    double acc = 0.0, acc2 = 0.0;
+    if (i0 < i1) {
+        int64_t q = pidx(n, i0, j);
+        for (int i = i0; i < i1; ++i) {
+            acc = acc + Rw[q];
+            P[q] = acc;
+            if (WITH_CT) acc2 = acc2 + v[q];
+            q += n - i - 2;
+        }
+    }
+    T[(int64_t)c * n + j] = acc;
+    if (WITH_CT) T2[(int64_t)c * n + j] = acc2;
+}
+
+template <bool WITH_CT>
+__global__ void k_colscan_carry(double* __restrict__ T, const double* __restrict__ T2, double* __restrict__ CT, int n, int nchunks,
+                                const int* done) {
     if (done && *done) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    if (j == 0) { if (WITH_CT) CT[0] = 0.0; return; }
-    double acc = 0.0, acc2 = 0.0;
-    int64_t q = j - 1;   // idx(0, j)
-    for (int i = 0; i < j; ++i) {
-        acc = acc + Rw[q];
-        P[q] = acc;
-        if (WITH_CT) acc2 = acc2 + v[q];
-        q += n - i - 2;  // idx(i+1, j) - idx(i, j)
+    double carry = 0.0, acc2 = 0.0;
+    for (int c = 0; c < nchunks; ++c) {   // T[c][j] becomes the exclusive carry of chunk c
+        const double t = T[(int64_t)c * n + j];
+        T[(int64_t)c * n + j] = carry;
+        carry = carry + t;
+        if (WITH_CT) acc2 = acc2 + T2[(int64_t)c * n + j];
     }
     if (WITH_CT) CT[j] = acc2;
 }
 
-__global__ void k_prs(const double* RT, const double* CT, double* PRS, int n, const int* done) {
+__global__ void k_colscan_fix(double* __restrict__ P, const double* __restrict__ T, int n, const int* done) {
     if (done && *done) return;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double acc = 0.0;
-    for (int a = 0; a < n; ++a) { acc = acc + (RT[a] + CT[a]); PRS[a] = acc; }
+    const int i = blockIdx.y;
+    if (i > n - 2) return;
+    const double* carry = T + (int64_t)(i / COL_CHUNK) * n;
+    const int64_t rs = row_start(n, i);
+    for (int j = i + 1 + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int64_t q = rs + (j - i - 1);
+        P[q] = carry[j] + P[q];
+    }
+}
+
+// PRS[a] = sum_{a' <= a} (RT[a'] + CT[a']), strictly left to right; operands staged through shared memory in parallel
+__global__ void __launch_bounds__(1024) k_prs(const double* RT, const double* CT, double* PRS, int n, const int* done) {
+    if (done && *done) return;
+    extern __shared__ double stage[];
+    for (int a = threadIdx.x; a < n; a += blockDim.x) stage[a] = RT[a] + CT[a];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int a = 0; a < n; ++a) { acc = acc + stage[a]; stage[a] = acc; }
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < n; a += blockDim.x) PRS[a] = stage[a];
 }
 
 // ---------------------------------------------------------------- fixed reduction tree (level 1 inside producers)
@@ -348,6 +392,8 @@ struct Csw {
     cudaStream_t st = nullptr;
     double *d = nullptr, *x = nullptr, *r = nullptr, *w = nullptr, *p = nullptr, *y = nullptr, *old_x = nullptr, *AtWd = nullptr;
     double *Rw = nullptr, *P = nullptr, *RT = nullptr, *CT = nullptr, *PRS = nullptr, *part1 = nullptr, *part2 = nullptr;
+    double *T = nullptr, *T2 = nullptr;   // column-scan chunk totals / carries
+    int nchunks = 0;
     unsigned char* active = nullptr;
     Scalars* sc = nullptr;
     Scalars* h_sc = nullptr;
@@ -361,6 +407,9 @@ struct Csw {
         CSW_ALLOC(d, np); CSW_ALLOC(x, np); CSW_ALLOC(r, np); CSW_ALLOC(w, np); CSW_ALLOC(p, np); CSW_ALLOC(y, np);
         CSW_ALLOC(old_x, np); CSW_ALLOC(AtWd, np); CSW_ALLOC(Rw, np); CSW_ALLOC(P, np);
         CSW_ALLOC(RT, n); CSW_ALLOC(CT, n); CSW_ALLOC(PRS, n);
+        nchunks = (n + COL_CHUNK - 1) / COL_CHUNK;
+        CSW_ALLOC(T, (size_t)nchunks * n); CSW_ALLOC(T2, (size_t)nchunks * n);
+        FNN_CUDA(cudaFuncSetAttribute(k_prs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * n)));
         CSW_ALLOC(part1, nblk + 1); CSW_ALLOC(part2, (nblk + 1023) / 1024 + 1);
         CSW_ALLOC(active, np); CSW_ALLOC(sc, 1);
         FNN_CUDA(cudaMallocHost((void**)&h_sc, sizeof(Scalars)));
@@ -371,7 +420,7 @@ struct Csw {
     void release() {
         if (cg_graph) cudaGraphExecDestroy(cg_graph);
         cudaFree(d); cudaFree(x); cudaFree(r); cudaFree(w); cudaFree(p); cudaFree(y); cudaFree(old_x); cudaFree(AtWd);
-        cudaFree(Rw); cudaFree(P); cudaFree(RT); cudaFree(CT); cudaFree(PRS); cudaFree(part1); cudaFree(part2);
+        cudaFree(T); cudaFree(T2); cudaFree(Rw); cudaFree(P); cudaFree(RT); cudaFree(CT); cudaFree(PRS); cudaFree(part1); cudaFree(part2);
         cudaFree(active); cudaFree(sc);
         if (h_sc) cudaFreeHost(h_sc);
         if (st) cudaStreamDestroy(st);
@@ -379,19 +428,26 @@ struct Csw {
     int grid1d(int64_t len, int threads) const { return (int)std::min<int64_t>((len + threads - 1) / threads, 148 * 16); }
     dim3 grid_rows() const { return dim3((unsigned)std::max(1, std::min((n + 255) / 256, 64)), (unsigned)(n - 1)); }
 
+    template <bool WITH_CT>
+    void colscan(const double* in, const int* gate) {
+        const dim3 g((unsigned)((n + 127) / 128), (unsigned)nchunks);
+        k_colscan_local<WITH_CT><<<g, 128, 0, st>>>(Rw, in, P, T, T2, n, gate);
+        k_colscan_carry<WITH_CT><<<(n + 127) / 128, 128, 0, st>>>(T, T2, CT, n, nchunks, gate);
+        k_colscan_fix<<<grid_rows(), 256, 0, st>>>(P, T, n, gate);
+    }
     // out = A in   (d = A b)
     void Ab(const double* in, double* out, const int* gate) {
         k_rowscan<<<std::min(n, 148 * 8), 256, 0, st>>>(in, Rw, nullptr, n, gate);
-        k_colscan<false><<<(n + 127) / 128, 128, 0, st>>>(Rw, in, P, nullptr, n, gate);
+        colscan<false>(in, gate);
         k_ab_combine<<<grid_rows(), 256, 0, st>>>(P, out, n, gate);
-        launches += 3;
+        launches += 5;
     }
     // G/PRS for A^T in
     void Atx_prefix(const double* in, const int* gate) {
         k_rowscan<<<std::min(n, 148 * 8), 256, 0, st>>>(in, Rw, RT, n, gate);
-        k_colscan<true><<<(n + 127) / 128, 128, 0, st>>>(Rw, in, P, CT, n, gate);
-        k_prs<<<1, 32, 0, st>>>(RT, CT, PRS, n, gate);
-        launches += 3;
+        colscan<true>(in, gate);
+        k_prs<<<1, 1024, sizeof(double) * n, st>>>(RT, CT, PRS, n, gate);
+        launches += 5;
     }
     void Atx(const double* in, double* out, const int* gate) {
         Atx_prefix(in, gate);
@@ -583,7 +639,7 @@ static int active_conjugate(Csw& c) {
 }  // namespace
 
 extern "C" int fnn_csw_matvec(const fnn_opts* o, int32_t which, const double* v, int64_t n, double* out) {
-    if (!v || !out || n < 4 || n > 30000) { fnn::set_error("fnn_csw_matvec: bad arguments"); return FNN_E_ARG; }
+    if (!v || !out || n < 4 || n > 20000) { fnn::set_error("fnn_csw_matvec: bad arguments"); return FNN_E_ARG; }
     int cnt = 0;
     if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) { cudaGetLastError(); fnn::set_error("no CUDA device available (libfastnn has no CPU fallback)"); return FNN_E_NODEVICE; }
     FNN_CUDA(cudaSetDevice(o ? o->device : 0));
@@ -607,7 +663,7 @@ extern "C" int fnn_csw_matvec(const fnn_opts* o, int32_t which, const double* v,
 
 extern "C" int fnn_split_weights(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double* x_out,
                                  int64_t* stats_out) {
-    if (!ordering || !d_upper || !x_out || n < 4 || n > 30000) { fnn::set_error("fnn_split_weights: bad arguments (4 <= n <= 30000)"); return FNN_E_ARG; }
+    if (!ordering || !d_upper || !x_out || n < 4 || n > 20000) { fnn::set_error("fnn_split_weights: bad arguments (4 <= n <= 20000)"); return FNN_E_ARG; }
     int cnt = 0;
     if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) { cudaGetLastError(); fnn::set_error("no CUDA device available (libfastnn has no CPU fallback)"); return FNN_E_NODEVICE; }
     FNN_CUDA(cudaSetDevice(o ? o->device : 0));

@@ -41,19 +41,25 @@ void rowscan(int64_t n, const double* v, double* Rw, double* RT) {
     }
     if (RT) RT[n - 1] = 0.0;
 }
-// k_colscan
+// k_colscan_local / k_colscan_carry / k_colscan_fix: chunks of 32 rows scanned from zero, sequential carry
 void colscan(int64_t n, const double* Rw, const double* v, double* P, double* CT) {
+    const int64_t CH = 32;
     if (CT) CT[0] = 0.0;
-    for (int64_t j = 1; j < n; ++j) {
-        double acc = 0.0, acc2 = 0.0;
-        int64_t q = j - 1;
-        for (int64_t i = 0; i < j; ++i) {
-            acc = acc + Rw[q];
-            P[q] = acc;
-            if (CT) acc2 = acc2 + v[q];
-            q += n - i - 2;
+    for (int64_t j = 0; j < n; ++j) {
+        double carry = 0.0, ct = 0.0;
+        for (int64_t i0 = 0; i0 < n; i0 += CH) {   // every chunk index exists for every column (empty chunks add 0.0)
+            const int64_t i1 = std::min(i0 + CH, j);
+            double acc = 0.0, acc2 = 0.0;
+            for (int64_t i = i0; i < i1; ++i) {
+                const int64_t q = pidx(n, i, j);
+                acc = acc + Rw[q];
+                P[q] = carry + acc;
+                if (CT) acc2 = acc2 + v[q];
+            }
+            carry = carry + acc;
+            if (CT) ct = ct + acc2;
         }
-        if (CT) CT[j] = acc2;
+        if (CT) CT[j] = ct;
     }
 }
 struct Work { std::vector<double> Rw, P, RT, CT, PRS; };
