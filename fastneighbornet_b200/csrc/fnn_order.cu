@@ -102,6 +102,7 @@ __device__ __forceinline__ bool better(double q, unsigned long long k, double bq
 }  // namespace
 #include <cuda.h>
 namespace {
+__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail);
 #include "fnn_scan_tma.cuh"
 #include "fnn_exact_sum.cuh"
 #include "fnn_modes.cuh"
@@ -418,8 +419,7 @@ __device__ __forceinline__ double duv_rule(bool uFirst, double dZX, double dYX, 
 // ------------------------------------------------------------------ K3a: selection result -> clusters (one warp)
 // Multi-GPU: merges the per-rank partial min-locs posted by every rank's scan.  Then Cx, Cy from the
 // (i, j) key (or from the Relaxed/Random strategy), the id-order swap of NetMakerOriginal.java:376-380.
-__global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
-    if (st->done || threadIdx.x != 0) return;
+__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
     const int m = st->m, P2 = st->P2;
     if (m == 4 && st->c == 2) { st->need_rx = 0; return; }   // special case is handled by k_pick
     const bool strategy = (st->mode != 0 && m > st->fallback);
@@ -448,6 +448,10 @@ __global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s
     st->cy = cy; st->cyn = cy < P2 ? (cy ^ 1) : -1;
     st->need_rx = (st->cxn >= 0 || st->cyn >= 0);
     if (!strategy) st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
+}
+__global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
+    if (st->done || threadIdx.x != 0) return;
+    select_body(id, p2s, st, mail);
 }
 
 // ------------------------------------------------------------------ K3b: stage the ComputeRx operands on all SMs
@@ -831,6 +835,9 @@ struct fnn_ctx {
     DevState* st = nullptr;
     Partial* partials = nullptr;
     int scan_grid = 0, row_grid = 0;
+    // the scan's last block also decodes Cx, Cy (saves the k_select launch) when nothing has to be merged or overridden
+    bool fused_select() const { return have_tmap && world == 1 && o.mode == FNN_CANONICAL; }
+    int launches_per_iter() const { return 6 + (fused_select() ? 0 : 1) + (o.mode >= FNN_RANDOM_N ? 2 : 0); }
     DevState* h_st = nullptr;  // pinned
     CUtensorMap tmap;
     bool have_tmap = false;
@@ -1025,7 +1032,7 @@ static_assert(PICK_THREADS == xsum::THREADS, "exact-sum block size");
 
 static inline void launch_scan(fnn_ctx* c) {
     if (c->have_tmap)
-        tma::k_scan_tma<<<c->sms, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials, c->peers);
+        tma::k_scan_tma<<<c->sms, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials, c->peers, c->id, c->p2s, c->fused_select() ? 1 : 0);
     else
         k_scan<32><<<c->scan_grid, SCAN_THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->partials);
 }
@@ -1056,7 +1063,7 @@ static inline void launch_rest(fnn_ctx* c) {
         modes::k_random_eval<<<c->sms * 2, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, c->pairs, c->walk, c->partials,
                                                                 c->walk_ticket);
     }
-    k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail);
+    if (!c->fused_select()) k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail);
     k_rx_stage<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->p2s, c->st, c->rxs, c->rxs_ld);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
                                                     c->serial_chain, c->rxs, c->rxs_ld);
@@ -1222,7 +1229,7 @@ static int run_relaxed(fnn_ctx* c, int64_t& launches) {
         int sel[2] = {mir.pos[Cx], mir.pos[Cy]};
         FNN_CUDA(cudaMemcpyAsync(&c->st->cx_pos, sel, sizeof(sel), cudaMemcpyHostToDevice, c->stream));
         launch_rest(c);
-        launches += 6;
+        launches += c->launches_per_iter() - 1;
         FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
         FNN_CUDA(cudaStreamSynchronize(c->stream));
         mir.apply(c->h_st->pick_x_id, c->h_st->pick_y_id);
@@ -1314,7 +1321,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
                 ++prof_samples;
             }
             launch_rest(c);
-            launches += 7; ++scans;
+            launches += c->launches_per_iter(); ++scans;
         }
         cudaEventDestroy(p0); cudaEventDestroy(p1);
         FNN_CUDA(cudaGetLastError());
@@ -1334,7 +1341,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
             const int64_t batch = 64;  // graphs between done-flag polls
             for (int64_t b = 0; b < batch && it < max_iters; ++b, it += GI) {
                 FNN_CUDA(cudaGraphLaunch(c->graph, c->stream));
-                launches += (7 + 2 * (c->o.mode >= FNN_RANDOM_N)) * GI; scans += GI;
+                launches += (int64_t)c->launches_per_iter() * GI; scans += GI;
             }
             FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
             FNN_CUDA(cudaStreamSynchronize(c->stream));
@@ -1345,7 +1352,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
         while (it < max_iters) {
             for (int b = 0; b < 256 && it < max_iters; ++b, ++it) {
                 launch_scan(c); launch_rest(c);
-                launches += 7; ++scans;
+                launches += c->launches_per_iter(); ++scans;
             }
             FNN_CUDA(cudaGetLastError());
             FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));

@@ -196,7 +196,8 @@ __device__ __forceinline__ void eval_pp(const double* sm, const RowData* rd, dou
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ Sx, const int* __restrict__ pos,
-           DevState* st, Partial* partials, const PeerTable* peers) {
+           DevState* st, Partial* partials, const PeerTable* peers, const int* __restrict__ ids, const int* __restrict__ p2s,
+           int fused_select) {
     if (st->done || (st->mode != 0 && st->m > st->fallback)) return;   // NetMakerOriginal.java:361-366
     extern __shared__ __align__(1024) unsigned char smem[];
     // keep the ring pointer in the shared window (no generic-address loads): offset, not integer cast
@@ -394,6 +395,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
                 st->selQ = bq;
                 st->sel_i = (int)(bk >> 32);
                 st->sel_j = (int)(bk & 0xffffffffu);
+                if (fused_select) select_body(ids, p2s, st, nullptr);   // Cx, Cy, id-order swap: saves a launch
             }
         }
     }
