@@ -399,6 +399,16 @@ struct Csw {
     Scalars* h_sc = nullptr;
     cudaGraphExec_t cg_graph = nullptr;
     int64_t cg_calls = 0, outer = 0, inner = 0, launches = 0, launches_per_graph = 0;
+    // cub scratch and the 60 % collapse work arrays
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    double *neg = nullptr, *neg_sorted = nullptr;
+    int *d_count = nullptr, *tie_flag = nullptr, *tie_rank = nullptr;
+    void* d_minloc = nullptr;
+    int ensure_tmp(size_t need) {
+        if (need > tmp_bytes) { if (tmp) cudaFree(tmp); tmp = nullptr; FNN_CUDA(cudaMalloc(&tmp, need)); tmp_bytes = need; }
+        return FNN_OK;
+    }
 
     int* done_ptr() { return &sc->done; }
 
@@ -412,6 +422,8 @@ struct Csw {
         FNN_CUDA(cudaFuncSetAttribute(k_prs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * n)));
         CSW_ALLOC(part1, nblk + 1); CSW_ALLOC(part2, (nblk + 1023) / 1024 + 1);
         CSW_ALLOC(active, np); CSW_ALLOC(sc, 1);
+        CSW_ALLOC(neg, np); CSW_ALLOC(neg_sorted, np); CSW_ALLOC(tie_flag, np); CSW_ALLOC(tie_rank, np); CSW_ALLOC(d_count, 1);
+        FNN_CUDA(cudaMalloc(&d_minloc, 16));
         FNN_CUDA(cudaMallocHost((void**)&h_sc, sizeof(Scalars)));
         FNN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         FNN_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
@@ -422,6 +434,7 @@ struct Csw {
         cudaFree(d); cudaFree(x); cudaFree(r); cudaFree(w); cudaFree(p); cudaFree(y); cudaFree(old_x); cudaFree(AtWd);
         cudaFree(T); cudaFree(T2); cudaFree(Rw); cudaFree(P); cudaFree(RT); cudaFree(CT); cudaFree(PRS); cudaFree(part1); cudaFree(part2);
         cudaFree(active); cudaFree(sc);
+        cudaFree(neg); cudaFree(neg_sorted); cudaFree(tie_flag); cudaFree(tie_rank); cudaFree(d_count); cudaFree(d_minloc); cudaFree(tmp);
         if (h_sc) cudaFreeHost(h_sc);
         if (st) cudaStreamDestroy(st);
     }
@@ -512,16 +525,13 @@ struct Csw {
 
 template <typename InOp>
 static int minloc_reduce(Csw& c, InOp op, MinLoc* out_host) {
-    static thread_local void* tmp = nullptr;
-    static thread_local size_t tmp_bytes = 0;
-    static thread_local MinLoc* d_out = nullptr;
-    if (!d_out) FNN_CUDA(cudaMalloc((void**)&d_out, sizeof(MinLoc)));
+    MinLoc* d_out = reinterpret_cast<MinLoc*>(c.d_minloc);
     cub::CountingInputIterator<long long> cnt(0);
     cub::TransformInputIterator<MinLoc, InOp, cub::CountingInputIterator<long long>> it(cnt, op);
     size_t need = 0;
     FNN_CUDA(cub::DeviceReduce::Reduce(nullptr, need, it, d_out, (int)c.np, MinLocOp(), MinLoc{0.0, -1}, c.st));
-    if (need > tmp_bytes) { if (tmp) cudaFree(tmp); FNN_CUDA(cudaMalloc(&tmp, need)); tmp_bytes = need; }
-    FNN_CUDA(cub::DeviceReduce::Reduce(tmp, need, it, d_out, (int)c.np, MinLocOp(), MinLoc{0.0, -1}, c.st));
+    if (c.ensure_tmp(need)) return FNN_E_CUDA;
+    FNN_CUDA(cub::DeviceReduce::Reduce(c.tmp, need, it, d_out, (int)c.np, MinLocOp(), MinLoc{0.0, -1}, c.st));
     FNN_CUDA(cudaMemcpyAsync(out_host, d_out, sizeof(MinLoc), cudaMemcpyDeviceToHost, c.st));
     FNN_CUDA(cudaStreamSynchronize(c.st));
     return FNN_OK;
@@ -529,24 +539,10 @@ static int minloc_reduce(Csw& c, InOp op, MinLoc* out_host) {
 
 // worstIndices(x, 0.6) + contraction (:282-330, :420-431); returns whether anything was contracted
 static int contract_worst(Csw& c, bool* contracted) {
-    static thread_local void* tmp = nullptr;
-    static thread_local size_t tmp_bytes = 0;
-    static thread_local double *neg = nullptr, *neg_sorted = nullptr;
-    static thread_local int *d_count = nullptr, *tie_flag = nullptr, *tie_rank = nullptr;
-    static thread_local int64_t cap = 0;
-    if (cap < c.np) {
-        if (neg) { cudaFree(neg); cudaFree(neg_sorted); cudaFree(tie_flag); cudaFree(tie_rank); cudaFree(d_count); }
-        FNN_CUDA(cudaMalloc((void**)&neg, sizeof(double) * c.np));
-        FNN_CUDA(cudaMalloc((void**)&neg_sorted, sizeof(double) * c.np));
-        FNN_CUDA(cudaMalloc((void**)&tie_flag, sizeof(int) * c.np));
-        FNN_CUDA(cudaMalloc((void**)&tie_rank, sizeof(int) * c.np));
-        FNN_CUDA(cudaMalloc((void**)&d_count, sizeof(int)));
-        cap = c.np;
-    }
-    auto ensure = [&](size_t need) -> int {
-        if (need > tmp_bytes) { if (tmp) cudaFree(tmp); FNN_CUDA(cudaMalloc(&tmp, need)); tmp_bytes = need; }
-        return FNN_OK;
-    };
+    double *neg = c.neg, *neg_sorted = c.neg_sorted;
+    int *d_count = c.d_count, *tie_flag = c.tie_flag, *tie_rank = c.tie_rank;
+    auto ensure = [&](size_t need) -> int { return c.ensure_tmp(need); };
+    void*& tmp = c.tmp;
     size_t need = 0;
     FNN_CUDA(cub::DeviceSelect::If(nullptr, need, c.x, neg, d_count, (int)c.np, IsNeg(), c.st));
     if (ensure(need)) return FNN_E_CUDA;

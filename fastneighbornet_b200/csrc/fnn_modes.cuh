@@ -290,12 +290,14 @@ k_random_eval(const double* __restrict__ D, int64_t ld, const double* __restrict
 }
 
 // ---------------------------------------------------------------- Relaxed findRowMin
-struct RowMinOut { double value; int count; int overflow; int pos[MAX_TIES]; };
+// result record; lives in host-mapped pinned memory (zero copy): the host spins on `seq`
+struct RowMinOut { double value; int count; int overflow; volatile int seq; int pad; int pos[MAX_TIES]; };
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_rowmin(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ p2s,
-         const DevState* st, int ip, RowMinOut* out) {
+         const DevState* st, int ip, RowMinOut* out, int seq) {
     __shared__ double wmin[THREADS / 32];
+    __shared__ int spos[MAX_TIES];
     __shared__ double gmin;
     __shared__ int cnt;
     const int m = st->m, P2 = st->P2, tid = threadIdx.x;
@@ -327,21 +329,29 @@ k_rowmin(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx
         const double q = (cm2 * dpq_roles(D, ld, sp, sq, P2) - Sp) - Sx[sq];
         if (q == g) {
             const int k = atomicAdd(&cnt, 1);
-            if (k < MAX_TIES) out->pos[k] = iq;
+            if (k < MAX_TIES) spos[k] = iq;
         }
     }
     __syncthreads();
+    const int nt = min(cnt, MAX_TIES);
     if (tid == 0) {
-        const int n = min(cnt, MAX_TIES);
-        for (int a = 1; a < n; ++a) {   // insertion sort: the list has one or two entries in practice
-            const int v = out->pos[a];
+        for (int a = 1; a < nt; ++a) {   // insertion sort: the list has one or two entries in practice
+            const int v = spos[a];
             int b = a - 1;
-            while (b >= 0 && out->pos[b] > v) { out->pos[b + 1] = out->pos[b]; --b; }
-            out->pos[b + 1] = v;
+            while (b >= 0 && spos[b] > v) { spos[b + 1] = spos[b]; --b; }
+            spos[b + 1] = v;
         }
+    }
+    __syncthreads();
+    for (int k = tid; k < nt; k += THREADS) out->pos[k] = spos[k];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
         out->value = g;
-        out->count = n;
+        out->count = nt;
         out->overflow = cnt > MAX_TIES;
+        __threadfence_system();
+        out->seq = seq;   // the host polls this word
     }
 }
 
@@ -350,11 +360,11 @@ k_rowmin(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx
 // findAgglomeratedQ (NeighborNetLocal.java:280-386) with agg3wayLocal (:388-414) / agg4wayLocal (:416-466):
 // simulate joining (Cx, Cy) and return the Q of the merged cluster against testNode, plus the Q before
 // the join (:241-245).  Cx, Cy are taken as selected (no id swap, as in the reference call at :245).
-struct LookOut { double origQ, newQ; };
+struct LookOut { double origQ, newQ; volatile int seq; int pad; };
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_lookahead(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ p2s,
-            const DevState* st, int cx_pos, int cy_pos, int test_pos, LookOut* out) {
+            const DevState* st, int cx_pos, int cy_pos, int test_pos, LookOut* out, int seq) {
     extern __shared__ unsigned char smem_raw[];
     xsum::Smem* xs = reinterpret_cast<xsum::Smem*>(smem_raw);
     __shared__ double rx[4], crs[1];
@@ -435,6 +445,8 @@ k_lookahead(const double* __restrict__ D, int64_t ld, const double* __restrict__
         const double A = ((double)c - 1.0) - 2.0;
         out->newQ = (A * cd - crs[0]) - (subtracted + cd);                                // :361 / :412 / :464
         out->origQ = (((double)c - 2.0) * dCxT - Sx[Cx]) - Sx[T];                         // :241-243
+        __threadfence_system();
+        out->seq = seq;
     }
 }
 

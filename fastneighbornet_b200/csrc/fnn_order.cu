@@ -77,6 +77,9 @@ struct DevState {
 
 struct Partial { double q; unsigned long long key; };
 
+// Relaxed: host <-> device hand-off through host-mapped pinned memory (zero copy, no memcpy/stream-sync per step)
+struct HostCtl { volatile int cx_pos, cy_pos; volatile int pick_x_id, pick_y_id, pick_m_new; volatile int seq; };
+
 // Multi-GPU selection exchange: every rank scans 1/world of the tiles and posts its partial
 // (Q, i, j) min-loc into slot [iteration parity][rank] of EVERY peer's mailbox with plain stores over
 // NVLink (peer memory mapped through CUDA IPC); the tag carries the iteration number.
@@ -102,7 +105,7 @@ __device__ __forceinline__ bool better(double q, unsigned long long k, double bq
 }  // namespace
 #include <cuda.h>
 namespace {
-__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail);
+__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail, const HostCtl* ctl);
 #include "fnn_scan_tma.cuh"
 #include "fnn_exact_sum.cuh"
 #include "fnn_modes.cuh"
@@ -419,7 +422,8 @@ __device__ __forceinline__ double duv_rule(bool uFirst, double dZX, double dYX, 
 // ------------------------------------------------------------------ K3a: selection result -> clusters (one warp)
 // Multi-GPU: merges the per-rank partial min-locs posted by every rank's scan.  Then Cx, Cy from the
 // (i, j) key (or from the Relaxed/Random strategy), the id-order swap of NetMakerOriginal.java:376-380.
-__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
+__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail,
+                            const HostCtl* ctl) {
     const int m = st->m, P2 = st->P2;
     if (m == 4 && st->c == 2) { st->need_rx = 0; return; }   // special case is handled by k_pick
     const bool strategy = (st->mode != 0 && m > st->fallback);
@@ -441,7 +445,8 @@ __device__ void select_body(const int* __restrict__ id, const int* __restrict__ 
         st->sel_j = (int)(bk & 0xffffffffu);
     }
     int cx, cy;
-    if (strategy) { cx = p2s[st->cx_pos]; cy = p2s[st->cy_pos]; }   // Relaxed / Random findNodes
+    if (strategy && ctl && st->mode == 1) { cx = p2s[ctl->cx_pos]; cy = p2s[ctl->cy_pos]; }   // Relaxed: chosen by the host
+    else if (strategy) { cx = p2s[st->cx_pos]; cy = p2s[st->cy_pos]; }                        // Random: k_random_eval
     else { cx = p2s[st->sel_i]; cy = p2s[st->sel_j]; }
     if (id[cx] > id[cy]) { int t = cx; cx = cy; cy = t; }
     st->cx = cx; st->cxn = cx < P2 ? (cx ^ 1) : -1;
@@ -449,9 +454,9 @@ __device__ void select_body(const int* __restrict__ id, const int* __restrict__ 
     st->need_rx = (st->cxn >= 0 || st->cyn >= 0);
     if (!strategy) st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
 }
-__global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
+__global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail, const HostCtl* ctl) {
     if (st->done || threadIdx.x != 0) return;
-    select_body(id, p2s, st, mail);
+    select_body(id, p2s, st, mail, ctl);
 }
 
 // ------------------------------------------------------------------ K3b: stage the ComputeRx operands on all SMs
@@ -483,7 +488,7 @@ constexpr int PICK_THREADS = 1024;
 
 __global__ void __launch_bounds__(PICK_THREADS, 1)
 k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState* st, int* amalg, double* trace, int serial_chain,
-       const double* __restrict__ rxs, int64_t rxs_ld) {
+       const double* __restrict__ rxs, int64_t rxs_ld, HostCtl* ctl) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[4][CH_TILE] = reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw);
     __shared__ double rx[4];
@@ -628,6 +633,11 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
     if (trace) trace[8 * (int64_t)st->iter + 6] = kind;
     st->kind = kind;
     st->pick_kind = kind;
+    if (ctl) {   // Relaxed: the host mirror needs the chosen nodes now, not after the update kernels
+        ctl->pick_x_id = st->pick_x_id; ctl->pick_y_id = st->pick_y_id; ctl->pick_m_new = st->m_new;
+        __threadfence_system();
+        ctl->seq = st->iter + 1;
+    }
     st->K = K;
     // publish the new layout's node tables (sources were captured above, so overlaps are safe)
     for (int k = 0; k < K; ++k) {
@@ -825,6 +835,8 @@ struct fnn_ctx {
     double* scratch = nullptr;
     double* stage = nullptr;
     double* rxs = nullptr;            // 4 staged ComputeRx rows, segment-transposed
+    HostCtl* ctl = nullptr;           // Relaxed: host-mapped control block (nullptr otherwise)
+    cudaGraphExec_t rest_graph = nullptr;
     int* nbrpos = nullptr;            // Random modes: neighbour position per position, the walk's (i, j) pairs
     int2* pairs = nullptr;
     modes::WalkState* walk = nullptr;
@@ -891,6 +903,8 @@ extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->o.device);
     if (c->graph) cudaGraphExecDestroy(c->graph);
+    if (c->rest_graph) cudaGraphExecDestroy(c->rest_graph);
+    if (c->ctl) cudaFreeHost(c->ctl);
     cudaFree(c->D); cudaFree(c->Sx); cudaFree(c->scratch); cudaFree(c->stage); cudaFree(c->rxs); cudaFree(c->trace);
     for (int r = 0; r < MAX_WORLD; ++r) if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
     cudaFree(c->mail); cudaFree(c->peers);
@@ -1063,10 +1077,10 @@ static inline void launch_rest(fnn_ctx* c) {
         modes::k_random_eval<<<c->sms * 2, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, c->pairs, c->walk, c->partials,
                                                                 c->walk_ticket);
     }
-    if (!c->fused_select()) k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail);
+    if (!c->fused_select()) k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail, c->ctl);
     k_rx_stage<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->p2s, c->st, c->rxs, c->rxs_ld);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
-                                                    c->serial_chain, c->rxs, c->rxs_ld);
+                                                    c->serial_chain, c->rxs, c->rxs_ld, c->ctl);
     k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
     k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage);
     k_chain<<<1, PICK_THREADS, CHAIN_SMEM, c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage, c->serial_chain);
@@ -1139,16 +1153,45 @@ static int run_relaxed(fnn_ctx* c, int64_t& launches) {
     std::vector<int> rowPerm(n);
     for (int i = 0; i < n; ++i) rowPerm[i] = i;
     int top = n - 1;
-    modes::RowMinOut* d_out = nullptr;
+    // zero-copy result records in host-mapped pinned memory: kernels write them over PCIe, the host polls `seq`
     modes::RowMinOut* h_out = nullptr;
-    FNN_CUDA(cudaMalloc((void**)&d_out, sizeof(modes::RowMinOut)));
-    FNN_CUDA(cudaMallocHost((void**)&h_out, sizeof(modes::RowMinOut)));
+    modes::LookOut* h_look = nullptr;
+    FNN_CUDA(cudaHostAlloc((void**)&h_out, sizeof(modes::RowMinOut), cudaHostAllocMapped));
+    FNN_CUDA(cudaHostAlloc((void**)&h_look, sizeof(modes::LookOut), cudaHostAllocMapped));
+    if (!c->ctl) FNN_CUDA(cudaHostAlloc((void**)&c->ctl, sizeof(HostCtl), cudaHostAllocMapped));
+    memset((void*)h_out, 0, 32);
+    memset((void*)h_look, 0, sizeof(modes::LookOut));
+    memset((void*)c->ctl, 0, sizeof(HostCtl));
+    modes::RowMinOut* d_out = nullptr;
     modes::LookOut* d_look = nullptr;
-    FNN_CUDA(cudaMalloc((void**)&d_look, sizeof(modes::LookOut)));
+    FNN_CUDA(cudaHostGetDevicePointer((void**)&d_out, h_out, 0));
+    FNN_CUDA(cudaHostGetDevicePointer((void**)&d_look, h_look, 0));
     FNN_CUDA(cudaFuncSetAttribute(modes::k_lookahead, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(xsum::Smem)));
+    int seq = 0;   // hand-off sequence number of the row-scan / look-ahead records
+    auto wait_seq = [&](volatile int* word, int want) -> int {
+        // poll the mapped word; surface CUDA errors instead of spinning forever
+        for (long long spins = 0;; ++spins) {
+            if (*word == want) return FNN_OK;
+            if ((spins & 0xFFFFF) == 0xFFFFF && cudaStreamQuery(c->stream) != cudaErrorNotReady) {
+                if (*word == want) return FNN_OK;
+                cudaError_t e = cudaStreamQuery(c->stream);
+                if (e != cudaSuccess) { fnn::set_error("relaxed: %s", cudaGetErrorString(e)); return FNN_E_CUDA; }
+                if (*word != want) { fnn::set_error("relaxed: device finished without publishing record %d", want); return FNN_E_STATE; }
+            }
+        }
+    };
+    if (!c->rest_graph) {   // the agglomeration event as one graph launch
+        cudaGraph_t g;
+        FNN_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        launch_rest(c);
+        FNN_CUDA(cudaStreamEndCapture(c->stream, &g));
+        FNN_CUDA(cudaGraphInstantiate(&c->rest_graph, g, 0));
+        cudaGraphDestroy(g);
+    }
     const bool additive = c->o.additive != 0;
     int rc = FNN_OK;
     int Cx = 0, Cy = 0;   // node ids; persist across iterations like the Java fields
+    int iter_no = 0;      // == DevState.iter + 1 after each event (relaxed runs first, so iterations count from 0)
     std::vector<std::vector<RowMinHost>> lists;
     while (mir.m > c->o.canonical_fallback && mir.m > 3) {
         std::vector<std::pair<int, int>> found;   // node id -> list index (HashMap with identity keys)
@@ -1158,14 +1201,11 @@ static int run_relaxed(fnn_ctx* c, int64_t& launches) {
             int li = lookup(p);
             if (li >= 0) return li;
             if (mir.nbr[p]) { li = lookup(mir.nbr[p]); if (li >= 0) return li; }
-            modes::k_rowmin<<<1, modes::THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, mir.pos[p], d_out);
+            ++seq;
+            modes::k_rowmin<<<1, modes::THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, mir.pos[p], d_out, seq);
             ++launches;
-            if (cudaMemcpyAsync(h_out, d_out, 16, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-                cudaStreamSynchronize(c->stream) != cudaSuccess) return -2;
+            if (wait_seq(&h_out->seq, seq)) return -2;
             if (h_out->overflow) return -3;
-            if (h_out->count > 0 &&
-                (cudaMemcpyAsync(h_out->pos, d_out->pos, sizeof(int) * h_out->count, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-                 cudaStreamSynchronize(c->stream) != cudaSuccess)) return -2;
             std::vector<RowMinHost> l;
             for (int k = 0; k < h_out->count; ++k) l.push_back({p, mir.act[h_out->pos[k]], h_out->value});
             lists.push_back(std::move(l));
@@ -1214,31 +1254,32 @@ static int run_relaxed(fnn_ctx* c, int64_t& launches) {
                 }
                 if (testNode == 0) { chosen = true; continue; }
                 if (mir.nbr[testNode] && mir.nbr[testNode] < testNode) testNode = mir.nbr[testNode];
+                ++seq;
                 modes::k_lookahead<<<1, modes::THREADS, sizeof(xsum::Smem), c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, mir.pos[Cx],
-                                                                                        mir.pos[Cy], mir.pos[testNode], d_look);
+                                                                                        mir.pos[Cy], mir.pos[testNode], d_look, seq);
                 ++launches;
-                modes::LookOut lk;
-                if (cudaMemcpyAsync(&lk, d_look, sizeof(lk), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-                    cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = FNN_E_CUDA; break; }
-                if (std::fabs(lk.origQ - lk.newQ) < .0000001) chosen = true;
+                if (wait_seq(&h_look->seq, seq)) { rc = FNN_E_CUDA; break; }
+                if (std::fabs(h_look->origQ - h_look->newQ) < .0000001) chosen = true;
             }
         }
         if (rc) break;
         if (Cx == 0 || Cy == 0) { fnn::set_error("relaxed selection found no pair"); rc = FNN_E_STATE; break; }
         // hand (Cx, Cy) to the device as positions, run the agglomeration event, read back the chosen nodes
-        int sel[2] = {mir.pos[Cx], mir.pos[Cy]};
-        FNN_CUDA(cudaMemcpyAsync(&c->st->cx_pos, sel, sizeof(sel), cudaMemcpyHostToDevice, c->stream));
-        launch_rest(c);
+        // hand (Cx, Cy) to the device through the mapped control block, run the agglomeration event (one graph launch) and
+        // pick up the chosen nodes as soon as k_pick has published them - the update kernels keep running behind
+        c->ctl->cx_pos = mir.pos[Cx];
+        c->ctl->cy_pos = mir.pos[Cy];
+        ++iter_no;
+        FNN_CUDA(cudaGraphLaunch(c->rest_graph, c->stream));
         launches += c->launches_per_iter() - 1;
-        FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
-        FNN_CUDA(cudaStreamSynchronize(c->stream));
-        mir.apply(c->h_st->pick_x_id, c->h_st->pick_y_id);
-        if (mir.m != c->h_st->m) { fnn::set_error("host mirror out of sync (m=%d vs %d)", mir.m, c->h_st->m); rc = FNN_E_STATE; break; }
+        if (wait_seq(&c->ctl->seq, iter_no)) { rc = FNN_E_CUDA; break; }
+        mir.apply(c->ctl->pick_x_id, c->ctl->pick_y_id);
+        if (mir.m != c->ctl->pick_m_new) { fnn::set_error("host mirror out of sync (m=%d vs %d)", mir.m, (int)c->ctl->pick_m_new); rc = FNN_E_STATE; break; }
     }
     if (rc == FNN_E_UNSUPPORTED) fnn::set_error("relaxed row scan: more than %d exact ties in one row", modes::MAX_TIES);
-    cudaFree(d_out);
-    cudaFree(d_look);
+    cudaStreamSynchronize(c->stream);
     cudaFreeHost(h_out);
+    cudaFreeHost(h_look);
     return rc;
 }
 

@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N scratch/mg_check.py : sharded-scan ordering must equal the single-GPU / oracle result."""
+"""torchrun --nproc-per-node N tests/mg_check.py : sharded-scan ordering must equal the single-GPU / oracle result."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

@@ -1,4 +1,4 @@
-"""Large-n run (BASELINE configs[4]: canonical, 100k taxa): torchrun or single process.  Prints time, algorithmic GB/s,
+"""tools/big_run.py <n> - Large-n run (BASELINE configs[4]: canonical, 100k taxa): torchrun or single process.  Prints time, algorithmic GB/s,
 permutation invariants and a hash of the ordering (all ranks must agree)."""
 import hashlib, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,3 +1,5 @@
+#!/bin/bash
+# smoke, default bench line, then the two ncu passes of B200_PROFILING.md (launch list + full capture of k_scan_tma)
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
 python bench.py > gpurun_out/bench_d.json 2> gpurun_out/bench_d.err; echo "bench rc=$?"; cat gpurun_out/bench_d.json | cut -c1-2500
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"

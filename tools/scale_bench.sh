@@ -1,3 +1,5 @@
+#!/bin/bash
+# tools/scale_bench.sh N : bench.py on N GPUs of one box (what the driver's scaling step runs), output in gpurun_out/
 N=$1
 if [ "$N" = "1" ]; then
   python bench.py --gpus 1 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/scale_$N.json 2> gpurun_out/scale_$N.err
