@@ -25,6 +25,7 @@ def lib():
     if _LIB is None:
         so = os.path.join(_HERE, "liboracle.so")
         srcs = [os.path.join(_HERE, f) for f in ("nnet_oracle.cpp", "csw_l1.cpp")]
+        srcs.append(os.path.join(os.path.dirname(_HERE), "fastneighbornet_b200", "csrc", "fnn_relaxed_sm.h"))
         if not os.path.exists(so) or any(os.path.exists(s_) and os.path.getmtime(s_) > os.path.getmtime(so) for s_ in srcs):
             build()
         L = ctypes.CDLL(so)
@@ -45,6 +46,7 @@ def lib():
         L.oracle_l1_tree_sum.argtypes = [c_dp, ctypes.c_int64]
         L.oracle_l1_tree_sum.restype = ctypes.c_double
         L.oracle_l1_split_weights.argtypes = [ctypes.c_int64, c_dp, c_dp, c_lp]
+        L.oracle_set_relaxed_sm.argtypes = [ctypes.c_int]
         L.oracle_java_random.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_ip]
         _LIB = L
     return _LIB
@@ -145,3 +147,9 @@ def l1_split_weights(n, d_pos):
     st = np.zeros(4, dtype=np.int64)
     lib().oracle_l1_split_weights(n, _dp(d), _dp(x), _lp(st))
     return x, {"cg_iters": int(st[0]), "cg_calls": int(st[1]), "outer": int(st[2]), "inner": int(st[3])}
+
+
+def set_relaxed_sm(on):
+    """Route the oracle's Relaxed findNodes through the PRODUCT's control state machine (csrc/fnn_relaxed_sm.h), with the
+    oracle's own row scans: used by tests to hold that state machine against the literal restatement on the CPU."""
+    lib().oracle_set_relaxed_sm(int(bool(on)))

@@ -28,7 +28,12 @@
 #include <unordered_map>
 #include <vector>
 
+// the PRODUCT's resumable state machine for the Relaxed control flow, compiled here for the CPU so that it can be
+// held against the literal findNodes below (tests/test_relaxed_sm_cpu.py); the oracle never depends on it otherwise
+#include "../fastneighbornet_b200/csrc/fnn_relaxed_sm.h"
+
 namespace {
+static int g_use_relaxed_sm = 0;
 
 // ---- java.util.Random (documented LCG) -------------------------------------
 // RNG contract for Relaxed/Random: the reference uses the unseedable
@@ -446,6 +451,61 @@ struct Engine {
         }
     }
 
+    // ---- Relaxed, driven by the product's state machine (fnn_relaxed_sm.h) with CPU row scans ----------------
+    relaxed::Machine SM{};
+    std::vector<int> sm_rowPerm, sm_epoch, sm_clist, sm_loff, sm_lcnt, sm_lme, sm_tie, sm_mymin;
+    bool sm_init = false;
+    struct SMView {
+        Engine* e; int num_active;
+        int m() const { return num_active; }
+        int id_at(int pos) const { return e->nd[e->act[pos]].id; }
+        int nbr_pos(int pos) const { int h = e->nd[e->act[pos]].nbr; return h < 0 ? -1 : e->nd[h].pos; }
+    };
+    void findNodesRelaxedSM(int num_active, int num_clusters) {
+        if (!sm_init) {
+            sm_rowPerm.assign(n, 0); sm_epoch.assign(n, 0); sm_clist.assign(n, 0);
+            sm_loff.assign(2 * n + 16, 0); sm_lcnt.assign(2 * n + 16, 0); sm_lme.assign(2 * n + 16, 0);
+            sm_tie.assign(16 * n + 65536, 0); sm_mymin.assign(2 * (8 * n + 65536), 0);
+            SM.rng = rng.s; SM.top = 0; SM.first_time = 1;
+            SM.rowPerm = sm_rowPerm.data(); SM.cache_epoch = sm_epoch.data(); SM.cache_list = sm_clist.data();
+            SM.list_off = sm_loff.data(); SM.list_cnt = sm_lcnt.data(); SM.list_me = sm_lme.data();
+            SM.tiepool = sm_tie.data(); SM.mymin = sm_mymin.data();
+            SM.max_lists = (int)sm_loff.size(); SM.tie_cap = (int)sm_tie.size(); SM.mymin_cap = (int)sm_mymin.size() / 2;
+            SM.epoch = 0; SM.additive = additive ? 1 : 0; SM.cx_pos = SM.cy_pos = -1;
+            sm_init = true;
+        }
+        SMView nv{this, num_active};
+        relaxed::begin_call(SM, (int)n);
+        int look_accept = 0;
+        while (true) {
+            const relaxed::Request rq = relaxed::step(SM, nv, look_accept);
+            if (rq == relaxed::REQ_DONE) break;
+            if (rq == relaxed::REQ_ERROR) { status = -11; break; }
+            if (rq == relaxed::REQ_SCAN) {
+                const int p = act[SM.req_pos];
+                double myMin = 1.7976931348623157e308;
+                int cnt = 0;
+                int* out = SM.tiepool + SM.tie_used;
+                const int room = relaxed::tie_room(SM);
+                for (int row = 0; row < num_active; ++row) {
+                    const int q = act[row];
+                    if (p == q || (nd[p].nbr >= 0 && nd[p].nbr == q)) continue;
+                    const double Qpq = ((double)num_clusters - 2.0) * clusterDist(p, q) - nd[p].Sx - nd[q].Sx;
+                    ++pair_evals;
+                    if (Qpq < myMin) { myMin = Qpq; cnt = 0; if (cnt < room) out[cnt] = row; cnt = 1; }
+                    else if (Qpq == myMin) { if (cnt < room) out[cnt] = row; ++cnt; }
+                }
+                if (cnt > room || !relaxed::commit_scan(SM, cnt)) { status = -12; break; }
+            } else {   // REQ_LOOKAHEAD
+                const int cx = act[SM.cx_pos], cy = act[SM.cy_pos], t = act[SM.look_test_pos];
+                const double originalQ = ((double)num_clusters - 2.0) * clusterDist(cx, t) - nd[cx].Sx - nd[t].Sx;
+                const double newQ = findAgglomeratedQ(cx, cy, t, num_clusters, num_active);
+                look_accept = std::fabs(originalQ - newQ) < .0000001;
+            }
+        }
+        if (SM.cx_pos >= 0 && SM.cy_pos >= 0) { Cx = act[SM.cx_pos]; Cy = act[SM.cy_pos]; }
+    }
+
     // ---- Random (NeighborNetRandom.java) -----------------------------------
     // :31-48
     int64_t findSearchAmount(int total) {
@@ -607,6 +667,7 @@ struct Engine {
             }
             if (mode == CANONICAL && threads > 1 && num_active > fallback) findNodesCanonicalMT(num_active, num_clusters);
             else if (num_active <= fallback || mode == CANONICAL) findNodesDefault(num_active, num_clusters);
+            else if (mode == RELAXED && g_use_relaxed_sm) findNodesRelaxedSM(num_active, num_clusters);
             else if (mode == RELAXED) findNodesRelaxed(num_active, num_clusters);
             else findNodesRandom(num_active, num_clusters);
             if (Cx < 0 || Cy < 0) { status = -10; return num_nodes; }
@@ -849,6 +910,9 @@ inline int64_t upperIndex(int64_t n, int64_t i, int64_t j) {   // DistancesAndNa
 }  // namespace
 
 extern "C" {
+
+// 1: Relaxed findNodes runs through the product's state machine (fnn_relaxed_sm.h) instead of the literal restatement
+void oracle_set_relaxed_sm(int on) { g_use_relaxed_sm = on; }
 
 // Ordering.  D is n*n row-major and is mutated in place (like the Java double[][]).
 // trace_out: optional [max_trace][8] doubles (m,c,cx,cy,x,y,kind,best); returns rows in *n_trace.
