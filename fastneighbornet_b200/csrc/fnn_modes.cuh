@@ -9,6 +9,7 @@
 //           position order and returns the minimum and every exact tie; the sampling / mutual-
 //           nearest logic of :170-264 is control flow and runs on the host (fnn_order.cu).
 #pragma once
+#include "fnn_relaxed_sm.h"
 
 namespace modes {
 
@@ -289,25 +290,23 @@ k_random_eval(const double* __restrict__ D, int64_t ld, const double* __restrict
     }
 }
 
-// ---------------------------------------------------------------- Relaxed findRowMin
-// result record; lives in host-mapped pinned memory (zero copy): the host spins on `seq`
-struct RowMinOut { double value; int count; int overflow; volatile int seq; int pad; int pos[MAX_TIES]; };
-
-__global__ void __launch_bounds__(THREADS, 1)
-k_rowmin(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ p2s,
-         const DevState* st, int ip, RowMinOut* out, int seq) {
+// ---------------------------------------------------------------- Relaxed findRowMin (block-wide device function)
+// Scans row `ip` over ALL active positions (NeighborNetLocal.java:100-126), writes the positions of every exact tie of
+// the minimum, in position order, to out[0..count) (global memory) and returns count (or -1 if more than `room`).
+__device__ int block_rowmin(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ pos,
+                            const int* __restrict__ p2s, int m, int P2, double cm2, int ip, int* out, int room) {
     __shared__ double wmin[THREADS / 32];
     __shared__ int spos[MAX_TIES];
     __shared__ double gmin;
     __shared__ int cnt;
-    const int m = st->m, P2 = st->P2, tid = threadIdx.x;
-    const double cm2 = (double)st->c - 2.0;
+    const int tid = threadIdx.x;
     const int sp = p2s[ip];
     const int spn = sp < P2 ? (sp ^ 1) : -1;
     const double Sp = Sx[sp];
     double mn = INFINITY;
-    for (int iq = tid; iq < m; iq += THREADS) {   // every active q except p and p.nbr (:100-105)
-        const int sq = p2s[iq];
+    // every active q except p and p.nbr (:100-105).  The minimum and the SET of its ties do not depend on the visiting
+    // order, so the block walks physical slots (coalesced rows) and orders the ties by position afterwards.
+    for (int sq = tid; sq < m; sq += THREADS) {
         if (sq == sp || sq == spn) continue;
         const double q = (cm2 * dpq_roles(D, ld, sp, sq, P2) - Sp) - Sx[sq];
         mn = fmin(mn, q);
@@ -323,17 +322,17 @@ k_rowmin(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx
     }
     __syncthreads();
     const double g = gmin;
-    for (int iq = tid; iq < m; iq += THREADS) {   // all exact ties (:118-124), gathered then ordered by position
-        const int sq = p2s[iq];
+    for (int sq = tid; sq < m; sq += THREADS) {   // all exact ties (:118-124), gathered then ordered by position
         if (sq == sp || sq == spn) continue;
         const double q = (cm2 * dpq_roles(D, ld, sp, sq, P2) - Sp) - Sx[sq];
         if (q == g) {
             const int k = atomicAdd(&cnt, 1);
-            if (k < MAX_TIES) spos[k] = iq;
+            if (k < MAX_TIES) spos[k] = pos[sq];
         }
     }
     __syncthreads();
-    const int nt = min(cnt, MAX_TIES);
+    const int total = cnt;
+    const int nt = min(total, MAX_TIES);
     if (tid == 0) {
         for (int a = 1; a < nt; ++a) {   // insertion sort: the list has one or two entries in practice
             const int v = spos[a];
@@ -343,33 +342,22 @@ k_rowmin(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx
         }
     }
     __syncthreads();
-    for (int k = tid; k < nt; k += THREADS) out->pos[k] = spos[k];
-    __threadfence_system();
+    if (total > MAX_TIES || total > room) return -1;
+    for (int k = tid; k < nt; k += THREADS) out[k] = spos[k];
     __syncthreads();
-    if (tid == 0) {
-        out->value = g;
-        out->count = nt;
-        out->overflow = cnt > MAX_TIES;
-        __threadfence_system();
-        out->seq = seq;   // the host polls this word
-    }
+    return nt;
 }
 
-
-// ---------------------------------------------------------------- Relaxed -additive look-ahead
+// ---------------------------------------------------------------- Relaxed -additive look-ahead (block-wide device function)
 // findAgglomeratedQ (NeighborNetLocal.java:280-386) with agg3wayLocal (:388-414) / agg4wayLocal (:416-466):
-// simulate joining (Cx, Cy) and return the Q of the merged cluster against testNode, plus the Q before
-// the join (:241-245).  Cx, Cy are taken as selected (no id swap, as in the reference call at :245).
-struct LookOut { double origQ, newQ; volatile int seq; int pad; };
-
-__global__ void __launch_bounds__(THREADS, 1)
-k_lookahead(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ p2s,
-            const DevState* st, int cx_pos, int cy_pos, int test_pos, LookOut* out, int seq) {
-    extern __shared__ unsigned char smem_raw[];
-    xsum::Smem* xs = reinterpret_cast<xsum::Smem*>(smem_raw);
+// simulate joining (Cx, Cy) and compare the Q of the merged cluster against testNode with the Q before the join
+// (:241-247).  Cx, Cy are taken as selected (no id swap, as in the reference call at :245).  Returns (in thread 0)
+// whether |originalQ - newQ| < 1e-7.
+__device__ bool block_lookahead(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ p2s,
+                                int m, int c, int P2, int cx_pos, int cy_pos, int test_pos, xsum::Smem* xs) {
     __shared__ double rx[4], crs[1];
     __shared__ int sh[2];
-    const int m = st->m, c = st->c, P2 = st->P2, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int Cx = p2s[cx_pos], Cy = p2s[cy_pos], T = p2s[test_pos];
     const int Cxn = Cx < P2 ? (Cx ^ 1) : -1, Cyn = Cy < P2 ? (Cy ^ 1) : -1;
     const int L = (m + xsum::THREADS - 1) / xsum::THREADS;
@@ -432,6 +420,7 @@ k_lookahead(const double* __restrict__ D, int64_t ld, const double* __restrict__
     };
     auto load1 = [&](int, int t, int k) -> double { return term(t * L + k); };
     xsum::block_exact_seq_sum<1>(xs, m, load1, [](int) { return true; }, crs);
+    bool accept = false;
     if (tid == 0) {
         const double dCxT = dpq_roles(D, ld, Cx, T, P2), dCyT = dpq_roles(D, ld, Cy, T, P2);
         const double subtracted = (Sx[T] - dCxT) - dCyT;                                  // :337
@@ -443,10 +432,65 @@ k_lookahead(const double* __restrict__ D, int64_t ld, const double* __restrict__
             cd = Tn >= 0 ? (d(x, T) + d(x, Tn)) * 0.5 : (d(T, x) + d(T, y)) * 0.5;
         } else cd = term(test_pos);
         const double A = ((double)c - 1.0) - 2.0;
-        out->newQ = (A * cd - crs[0]) - (subtracted + cd);                                // :361 / :412 / :464
-        out->origQ = (((double)c - 2.0) * dCxT - Sx[Cx]) - Sx[T];                         // :241-243
-        __threadfence_system();
-        out->seq = seq;
+        const double newQ = (A * cd - crs[0]) - (subtracted + cd);                        // :361 / :412 / :464
+        const double origQ = (((double)c - 2.0) * dCxT - Sx[Cx]) - Sx[T];                 // :241-243
+        accept = fabs(origQ - newQ) < .0000001;                                            // :247
+    }
+    return accept;
+}
+
+// ---------------------------------------------------------------- Relaxed findNodes: one kernel per iteration
+// One lane advances the control state machine of fnn_relaxed_sm.h (the code the CPU tests hold against the literal
+// oracle); whenever it asks for a row scan or a look-ahead, the whole block does it and resumes the machine.  No host
+// round trip: Relaxed is as device-resident and graph-replayable as the other modes.
+struct DevNodeView {
+    const int* id; const int* pos; const int* p2s; int m_, P2;
+    __device__ int m() const { return m_; }
+    __device__ int id_at(int p) const { return id[p2s[p]]; }
+    __device__ int nbr_pos(int p) const { const int s = p2s[p]; return s < P2 ? pos[s ^ 1] : -1; }
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_relaxed_select(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ id,
+                 const int* __restrict__ pos, const int* __restrict__ p2s, DevState* st, relaxed::Machine* Mg, int ntax) {
+    if (st->done || st->mode != 1 || st->m <= st->fallback) return;
+    extern __shared__ unsigned char smem_raw[];
+    xsum::Smem* xs = reinterpret_cast<xsum::Smem*>(smem_raw);
+    __shared__ relaxed::Machine M;
+    __shared__ int req, look_accept;
+    const int m = st->m, c = st->c, P2 = st->P2, tid = threadIdx.x;
+    const double cm2 = (double)c - 2.0;
+    const DevNodeView nv{id, pos, p2s, m, P2};
+    if (tid == 0) {
+        M = *Mg;
+        relaxed::begin_call(M, ntax);
+        look_accept = 0;
+    }
+    __syncthreads();
+    while (true) {
+        if (tid == 0) req = (int)relaxed::step(M, nv, look_accept);
+        __syncthreads();
+        const int r = req;
+        if (r == relaxed::REQ_DONE || r == relaxed::REQ_ERROR) break;
+        if (r == relaxed::REQ_SCAN) {
+            const int cnt = block_rowmin(D, ld, Sx, pos, p2s, m, P2, cm2, M.req_pos, M.tiepool + M.tie_used, relaxed::tie_room(M));
+            if (tid == 0) {
+                if (cnt < 0) M.error = 3;
+                else relaxed::commit_scan(M, cnt);
+            }
+        } else {
+            const bool acc = block_lookahead(D, ld, Sx, p2s, m, c, P2, M.cx_pos, M.cy_pos, M.look_test_pos, xs);
+            if (tid == 0) look_accept = acc ? 1 : 0;
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (M.error) break;
+    }
+    if (tid == 0) {
+        st->cx_pos = M.cx_pos;
+        st->cy_pos = M.cy_pos;
+        if (M.error || M.cx_pos < 0 || M.cy_pos < 0) { st->error = 10 + M.error; st->done = 1; st->skip = 1; }
+        *Mg = M;
     }
 }
 

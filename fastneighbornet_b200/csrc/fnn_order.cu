@@ -36,6 +36,7 @@
 #include <algorithm>
 #include "fastnn.h"
 #include "fnn_common.h"
+#include "fnn_relaxed_sm.h"
 
 namespace {
 
@@ -47,6 +48,7 @@ struct DevState {
     // committed state
     int m, c, P2, num_nodes;
     int iter, done, n_amalg, skip;
+    int error;                    // non-zero: a device-side strategy kernel gave up (pool overflow, no pair found)
     // selection result (k_scan)
     double selQ;
     int sel_i, sel_j;
@@ -77,8 +79,6 @@ struct DevState {
 
 struct Partial { double q; unsigned long long key; };
 
-// Relaxed: host <-> device hand-off through host-mapped pinned memory (zero copy, no memcpy/stream-sync per step)
-struct HostCtl { volatile int cx_pos, cy_pos; volatile int pick_x_id, pick_y_id, pick_m_new; volatile int seq; };
 
 // Multi-GPU selection exchange: every rank scans 1/world of the tiles and posts its partial
 // (Q, i, j) min-loc into slot [iteration parity][rank] of EVERY peer's mailbox with plain stores over
@@ -105,7 +105,7 @@ __device__ __forceinline__ bool better(double q, unsigned long long k, double bq
 }  // namespace
 #include <cuda.h>
 namespace {
-__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail, const HostCtl* ctl);
+__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail);
 #include "fnn_scan_tma.cuh"
 #include "fnn_exact_sum.cuh"
 #include "fnn_modes.cuh"
@@ -422,8 +422,7 @@ __device__ __forceinline__ double duv_rule(bool uFirst, double dZX, double dYX, 
 // ------------------------------------------------------------------ K3a: selection result -> clusters (one warp)
 // Multi-GPU: merges the per-rank partial min-locs posted by every rank's scan.  Then Cx, Cy from the
 // (i, j) key (or from the Relaxed/Random strategy), the id-order swap of NetMakerOriginal.java:376-380.
-__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail,
-                            const HostCtl* ctl) {
+__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
     const int m = st->m, P2 = st->P2;
     if (m == 4 && st->c == 2) { st->need_rx = 0; return; }   // special case is handled by k_pick
     const bool strategy = (st->mode != 0 && m > st->fallback);
@@ -445,8 +444,7 @@ __device__ void select_body(const int* __restrict__ id, const int* __restrict__ 
         st->sel_j = (int)(bk & 0xffffffffu);
     }
     int cx, cy;
-    if (strategy && ctl && st->mode == 1) { cx = p2s[ctl->cx_pos]; cy = p2s[ctl->cy_pos]; }   // Relaxed: chosen by the host
-    else if (strategy) { cx = p2s[st->cx_pos]; cy = p2s[st->cy_pos]; }                        // Random: k_random_eval
+    if (strategy) { cx = p2s[st->cx_pos]; cy = p2s[st->cy_pos]; }   // Relaxed: k_relaxed_select, Random: k_random_eval
     else { cx = p2s[st->sel_i]; cy = p2s[st->sel_j]; }
     if (id[cx] > id[cy]) { int t = cx; cx = cy; cy = t; }
     st->cx = cx; st->cxn = cx < P2 ? (cx ^ 1) : -1;
@@ -454,9 +452,9 @@ __device__ void select_body(const int* __restrict__ id, const int* __restrict__ 
     st->need_rx = (st->cxn >= 0 || st->cyn >= 0);
     if (!strategy) st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
 }
-__global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail, const HostCtl* ctl) {
+__global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
     if (st->done || threadIdx.x != 0) return;
-    select_body(id, p2s, st, mail, ctl);
+    select_body(id, p2s, st, mail);
 }
 
 // ------------------------------------------------------------------ K3b: stage the ComputeRx operands on all SMs
@@ -488,7 +486,7 @@ constexpr int PICK_THREADS = 1024;
 
 __global__ void __launch_bounds__(PICK_THREADS, 1)
 k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState* st, int* amalg, double* trace, int serial_chain,
-       const double* __restrict__ rxs, int64_t rxs_ld, HostCtl* ctl) {
+       const double* __restrict__ rxs, int64_t rxs_ld) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[4][CH_TILE] = reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw);
     __shared__ double rx[4];
@@ -633,11 +631,6 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
     if (trace) trace[8 * (int64_t)st->iter + 6] = kind;
     st->kind = kind;
     st->pick_kind = kind;
-    if (ctl) {   // Relaxed: the host mirror needs the chosen nodes now, not after the update kernels
-        ctl->pick_x_id = st->pick_x_id; ctl->pick_y_id = st->pick_y_id; ctl->pick_m_new = st->m_new;
-        __threadfence_system();
-        ctl->seq = st->iter + 1;
-    }
     st->K = K;
     // publish the new layout's node tables (sources were captured above, so overlaps are safe)
     for (int k = 0; k < K; ++k) {
@@ -835,8 +828,10 @@ struct fnn_ctx {
     double* scratch = nullptr;
     double* stage = nullptr;
     double* rxs = nullptr;            // 4 staged ComputeRx rows, segment-transposed
-    HostCtl* ctl = nullptr;           // Relaxed: host-mapped control block (nullptr otherwise)
-    cudaGraphExec_t rest_graph = nullptr;
+    relaxed::Machine* rl_machine = nullptr;   // Relaxed: the control state machine and its work arrays (device)
+    int *rl_rowPerm = nullptr, *rl_epoch = nullptr, *rl_clist = nullptr, *rl_loff = nullptr, *rl_lcnt = nullptr, *rl_lme = nullptr;
+    int *rl_tie = nullptr, *rl_mymin = nullptr;
+    int rl_max_lists = 0, rl_tie_cap = 0, rl_mymin_cap = 0;
     int* nbrpos = nullptr;            // Random modes: neighbour position per position, the walk's (i, j) pairs
     int2* pairs = nullptr;
     modes::WalkState* walk = nullptr;
@@ -849,7 +844,7 @@ struct fnn_ctx {
     int scan_grid = 0, row_grid = 0;
     // the scan's last block also decodes Cx, Cy (saves the k_select launch) when nothing has to be merged or overridden
     bool fused_select() const { return have_tmap && world == 1 && o.mode == FNN_CANONICAL; }
-    int launches_per_iter() const { return 6 + (fused_select() ? 0 : 1) + (o.mode >= FNN_RANDOM_N ? 2 : 0); }
+    int launches_per_iter() const { return 6 + (fused_select() ? 0 : 1) + (o.mode >= FNN_RANDOM_N ? 2 : 0) + (o.mode == FNN_RELAXED ? 1 : 0); }
     DevState* h_st = nullptr;  // pinned
     CUtensorMap tmap;
     bool have_tmap = false;
@@ -903,8 +898,8 @@ extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->o.device);
     if (c->graph) cudaGraphExecDestroy(c->graph);
-    if (c->rest_graph) cudaGraphExecDestroy(c->rest_graph);
-    if (c->ctl) cudaFreeHost(c->ctl);
+    cudaFree(c->rl_machine); cudaFree(c->rl_rowPerm); cudaFree(c->rl_epoch); cudaFree(c->rl_clist); cudaFree(c->rl_loff);
+    cudaFree(c->rl_lcnt); cudaFree(c->rl_lme); cudaFree(c->rl_tie); cudaFree(c->rl_mymin);
     cudaFree(c->D); cudaFree(c->Sx); cudaFree(c->scratch); cudaFree(c->stage); cudaFree(c->rxs); cudaFree(c->trace);
     for (int r = 0; r < MAX_WORLD; ++r) if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
     cudaFree(c->mail); cudaFree(c->peers);
@@ -966,6 +961,15 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     c->row_grid = std::max<int>(1, std::min<int64_t>((n + 255) / 256, c->sms * 4));
     FNN_ALLOC(c->partials, sizeof(Partial) * c->scan_grid);
     if (o->record_trace) FNN_ALLOC(c->trace, sizeof(double) * 8 * (n + 8));
+    if (o->mode == FNN_RELAXED) {
+        c->rl_max_lists = (int)(2 * n + 16); c->rl_tie_cap = (int)(16 * n + 65536); c->rl_mymin_cap = (int)(8 * n + 65536);
+        FNN_ALLOC(c->rl_machine, sizeof(relaxed::Machine));
+        FNN_ALLOC(c->rl_rowPerm, sizeof(int) * n); FNN_ALLOC(c->rl_epoch, sizeof(int) * n); FNN_ALLOC(c->rl_clist, sizeof(int) * n);
+        FNN_ALLOC(c->rl_loff, sizeof(int) * c->rl_max_lists); FNN_ALLOC(c->rl_lcnt, sizeof(int) * c->rl_max_lists);
+        FNN_ALLOC(c->rl_lme, sizeof(int) * c->rl_max_lists);
+        FNN_ALLOC(c->rl_tie, sizeof(int) * c->rl_tie_cap); FNN_ALLOC(c->rl_mymin, sizeof(int) * 2 * c->rl_mymin_cap);
+        FNN_CUDA(cudaFuncSetAttribute(modes::k_relaxed_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(xsum::Smem)));
+    }
     if (o->mode >= FNN_RANDOM_N) {
         int lg = 0;
         for (long long p10 = 1; p10 < n; p10 *= 10) ++lg;
@@ -1077,211 +1081,18 @@ static inline void launch_rest(fnn_ctx* c) {
         modes::k_random_eval<<<c->sms * 2, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, c->pairs, c->walk, c->partials,
                                                                 c->walk_ticket);
     }
-    if (!c->fused_select()) k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail, c->ctl);
+    if (c->o.mode == FNN_RELAXED)
+        modes::k_relaxed_select<<<1, modes::THREADS, sizeof(xsum::Smem), c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st,
+                                                                                     c->rl_machine, (int)c->n);
+    if (!c->fused_select()) k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail);
     k_rx_stage<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->p2s, c->st, c->rxs, c->rxs_ld);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
-                                                    c->serial_chain, c->rxs, c->rxs_ld, c->ctl);
+                                                    c->serial_chain, c->rxs, c->rxs_ld);
     k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
     k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage);
     k_chain<<<1, PICK_THREADS, CHAIN_SMEM, c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage, c->serial_chain);
 }
 
-
-// ---------------------------------------------------------------- Relaxed: host control flow
-// The sampling / mutual-nearest logic of NeighborNetLocal.findNodes (NeighborNetLocal.java:170-264) is
-// branchy control flow over a handful of row scans per iteration; it runs here on the host against a
-// mirror of the reference's node table, calling k_rowmin for every findRowMin (:88-157).
-namespace {
-struct JavaRandomHost {   // java.util.Random(seed), same stream as the device generator
-    uint64_t s;
-    explicit JavaRandomHost(int64_t seed) { s = ((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1); }
-    int32_t next(int bits) { s = (s * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1); return (int32_t)((int64_t)s >> (48 - bits)); }
-    int32_t nextInt(int32_t bound) {
-        int32_t r = next(31);
-        const int32_t m = bound - 1;
-        if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
-        for (int32_t u = r;; u = next(31)) {
-            r = u % bound;
-            if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) break;
-        }
-        return r;
-    }
-};
-
-struct Mirror {   // ids, neighbours and positions only; distances and row sums stay on the device
-    std::vector<int> pos, nbr;   // by node id (1-based); nbr 0 = none
-    std::vector<int> act;        // netNodes[]: node id per position
-    int m = 0, c = 0, nn = 0;
-    void init(int n) {
-        pos.assign(3 * n + 8, -1); nbr.assign(3 * n + 8, 0); act.assign(n, 0);
-        for (int i = 1; i <= n; ++i) { pos[i] = i - 1; act[i - 1] = i; }
-        m = c = nn = n;
-    }
-    int agg3(int x, int y, int z, int num_active) {   // position bookkeeping of agg3way (NetMakerOriginal.java:608-648)
-        const int u = nn + 1, v = nn + 2;
-        nn += 2;
-        act[pos[x]] = u; pos[u] = pos[x];
-        act[pos[z]] = v; pos[v] = pos[z];
-        const int last = act[num_active - 1];
-        act[pos[y]] = last; pos[last] = pos[y];
-        act[num_active - 1] = 0;
-        nbr[u] = v; nbr[v] = u;
-        return u;
-    }
-    void apply(int x, int y) {   // handleAgglomerationEvent's dispatch (:462-488)
-        if (nbr[x] == 0 && nbr[y] == 0) { nbr[x] = y; nbr[y] = x; }
-        else if (nbr[x] == 0) { agg3(x, y, nbr[y], m); m -= 1; }
-        else if (nbr[y] == 0 || m == 4) { agg3(y, x, nbr[x], m); m -= 1; }
-        else {
-            const int x2 = nbr[x], y2 = nbr[y];
-            const int u = agg3(x2, x, y, m);
-            agg3(u, nbr[u], y2, m - 1);
-            m -= 2;
-        }
-        c -= 1;
-    }
-};
-
-struct RowMinHost { int me, row; double value; };
-}  // namespace
-
-static int run_relaxed(fnn_ctx* c, int64_t& launches) {
-    const int n = (int)c->n;
-    Mirror mir;
-    mir.init(n);
-    JavaRandomHost rng((int64_t)c->o.seed);
-    std::vector<int> rowPerm(n);
-    for (int i = 0; i < n; ++i) rowPerm[i] = i;
-    int top = n - 1;
-    // zero-copy result records in host-mapped pinned memory: kernels write them over PCIe, the host polls `seq`
-    modes::RowMinOut* h_out = nullptr;
-    modes::LookOut* h_look = nullptr;
-    FNN_CUDA(cudaHostAlloc((void**)&h_out, sizeof(modes::RowMinOut), cudaHostAllocMapped));
-    FNN_CUDA(cudaHostAlloc((void**)&h_look, sizeof(modes::LookOut), cudaHostAllocMapped));
-    if (!c->ctl) FNN_CUDA(cudaHostAlloc((void**)&c->ctl, sizeof(HostCtl), cudaHostAllocMapped));
-    memset((void*)h_out, 0, 32);
-    memset((void*)h_look, 0, sizeof(modes::LookOut));
-    memset((void*)c->ctl, 0, sizeof(HostCtl));
-    modes::RowMinOut* d_out = nullptr;
-    modes::LookOut* d_look = nullptr;
-    FNN_CUDA(cudaHostGetDevicePointer((void**)&d_out, h_out, 0));
-    FNN_CUDA(cudaHostGetDevicePointer((void**)&d_look, h_look, 0));
-    FNN_CUDA(cudaFuncSetAttribute(modes::k_lookahead, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(xsum::Smem)));
-    int seq = 0;   // hand-off sequence number of the row-scan / look-ahead records
-    auto wait_seq = [&](volatile int* word, int want) -> int {
-        // poll the mapped word; surface CUDA errors instead of spinning forever
-        for (long long spins = 0;; ++spins) {
-            if (*word == want) return FNN_OK;
-            if ((spins & 0xFFFFF) == 0xFFFFF && cudaStreamQuery(c->stream) != cudaErrorNotReady) {
-                if (*word == want) return FNN_OK;
-                cudaError_t e = cudaStreamQuery(c->stream);
-                if (e != cudaSuccess) { fnn::set_error("relaxed: %s", cudaGetErrorString(e)); return FNN_E_CUDA; }
-                if (*word != want) { fnn::set_error("relaxed: device finished without publishing record %d", want); return FNN_E_STATE; }
-            }
-        }
-    };
-    if (!c->rest_graph) {   // the agglomeration event as one graph launch
-        cudaGraph_t g;
-        FNN_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        launch_rest(c);
-        FNN_CUDA(cudaStreamEndCapture(c->stream, &g));
-        FNN_CUDA(cudaGraphInstantiate(&c->rest_graph, g, 0));
-        cudaGraphDestroy(g);
-    }
-    const bool additive = c->o.additive != 0;
-    int rc = FNN_OK;
-    int Cx = 0, Cy = 0;   // node ids; persist across iterations like the Java fields
-    int iter_no = 0;      // == DevState.iter + 1 after each event (relaxed runs first, so iterations count from 0)
-    std::vector<std::vector<RowMinHost>> lists;
-    while (mir.m > c->o.canonical_fallback && mir.m > 3) {
-        std::vector<std::pair<int, int>> found;   // node id -> list index (HashMap with identity keys)
-        lists.clear();
-        auto lookup = [&](int node) -> int { for (auto& kv : found) if (kv.first == node) return kv.second; return -1; };
-        auto findRowMin = [&](int p) -> int {
-            int li = lookup(p);
-            if (li >= 0) return li;
-            if (mir.nbr[p]) { li = lookup(mir.nbr[p]); if (li >= 0) return li; }
-            ++seq;
-            modes::k_rowmin<<<1, modes::THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, mir.pos[p], d_out, seq);
-            ++launches;
-            if (wait_seq(&h_out->seq, seq)) return -2;
-            if (h_out->overflow) return -3;
-            std::vector<RowMinHost> l;
-            for (int k = 0; k < h_out->count; ++k) l.push_back({p, mir.act[h_out->pos[k]], h_out->value});
-            lists.push_back(std::move(l));
-            found.push_back({p, (int)lists.size() - 1});
-            return (int)lists.size() - 1;
-        };
-        std::vector<RowMinHost> myMinimums;
-        bool chosen = false;
-        for (int i = top + 1; i > 0 && !chosen; i--) {   // :185-260
-            const int swapCell = rng.nextInt(i);
-            if (rowPerm[swapCell] >= mir.m) {
-                std::swap(rowPerm[swapCell], rowPerm[top]);
-                if (i == top + 1) i--; else i++;
-                top--;
-                continue;
-            }
-            std::swap(rowPerm[i - 1], rowPerm[swapCell]);
-            const int p = mir.act[rowPerm[i - 1]];
-            if (mir.nbr[p] && mir.nbr[p] < p) continue;
-            const int li = findRowMin(p);
-            if (li < 0) { rc = li == -3 ? FNN_E_UNSUPPORTED : FNN_E_CUDA; break; }
-            for (size_t a = 0; a < lists[li].size(); ++a) {
-                const RowMinHost myRM = lists[li][a];
-                const int lo = findRowMin(myRM.row);
-                if (lo < 0) { rc = lo == -3 ? FNN_E_UNSUPPORTED : FNN_E_CUDA; break; }
-                for (size_t b = 0; b < lists[lo].size(); ++b) {
-                    const RowMinHost t = lists[lo][b];
-                    const int rn = mir.nbr[t.row], pn = mir.nbr[p];
-                    if (t.row == p || (rn && rn == p) || (rn && pn && rn == pn) || (pn && t.row == pn)) { myMinimums.push_back(t); break; }
-                }
-            }
-            if (rc) break;
-            if (!myMinimums.empty()) {
-                const RowMinHost pick = myMinimums[rng.nextInt((int)myMinimums.size())];
-                Cx = pick.me; Cy = pick.row;
-                if (!additive) { chosen = true; continue; }   // break outerloop (:257)
-                // -additive (:223-255): accept the join only if it leaves Q against a third cluster unchanged.  The
-                // reference repeats the identical test myMinimums.size() times (Cx, Cy are not re-read, :250-254), so one
-                // evaluation decides.  testNode: last active node outside both clusters (intended loop).
-                int testNode = 0;
-                for (int j = mir.m - 1; j >= 0; --j) {
-                    const int t = mir.act[j];
-                    if (t == Cx || t == Cy || t == mir.nbr[Cx] || t == mir.nbr[Cy]) continue;
-                    testNode = t;
-                    break;
-                }
-                if (testNode == 0) { chosen = true; continue; }
-                if (mir.nbr[testNode] && mir.nbr[testNode] < testNode) testNode = mir.nbr[testNode];
-                ++seq;
-                modes::k_lookahead<<<1, modes::THREADS, sizeof(xsum::Smem), c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, mir.pos[Cx],
-                                                                                        mir.pos[Cy], mir.pos[testNode], d_look, seq);
-                ++launches;
-                if (wait_seq(&h_look->seq, seq)) { rc = FNN_E_CUDA; break; }
-                if (std::fabs(h_look->origQ - h_look->newQ) < .0000001) chosen = true;
-            }
-        }
-        if (rc) break;
-        if (Cx == 0 || Cy == 0) { fnn::set_error("relaxed selection found no pair"); rc = FNN_E_STATE; break; }
-        // hand (Cx, Cy) to the device as positions, run the agglomeration event, read back the chosen nodes
-        // hand (Cx, Cy) to the device through the mapped control block, run the agglomeration event (one graph launch) and
-        // pick up the chosen nodes as soon as k_pick has published them - the update kernels keep running behind
-        c->ctl->cx_pos = mir.pos[Cx];
-        c->ctl->cy_pos = mir.pos[Cy];
-        ++iter_no;
-        FNN_CUDA(cudaGraphLaunch(c->rest_graph, c->stream));
-        launches += c->launches_per_iter() - 1;
-        if (wait_seq(&c->ctl->seq, iter_no)) { rc = FNN_E_CUDA; break; }
-        mir.apply(c->ctl->pick_x_id, c->ctl->pick_y_id);
-        if (mir.m != c->ctl->pick_m_new) { fnn::set_error("host mirror out of sync (m=%d vs %d)", mir.m, (int)c->ctl->pick_m_new); rc = FNN_E_STATE; break; }
-    }
-    if (rc == FNN_E_UNSUPPORTED) fnn::set_error("relaxed row scan: more than %d exact ties in one row", modes::MAX_TIES);
-    cudaStreamSynchronize(c->stream);
-    cudaFreeHost(h_out);
-    cudaFreeHost(h_look);
-    return rc;
-}
 
 // expandNodes (NetMakerOriginal.java:246-325) on the host from the amalgamation log
 static void expand_order(int64_t n, const std::vector<int>& lg, int n_amalg, const int* final3, int32_t* ordering) {
@@ -1334,9 +1145,19 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     double prof_ms = 0.0, prof_bytes = 0.0;
     int64_t prof_samples = 0;
 
-    if (c->o.mode == FNN_RELAXED && n > c->o.canonical_fallback) {
-        int rrc = run_relaxed(c, launches);   // until num_active <= canonical_fallback; the tail below is canonical
-        if (rrc) return rrc;
+    if (c->o.mode == FNN_RELAXED) {   // (re)initialise the device-side control state machine (NeighborNetLocal.java:26-32)
+        relaxed::Machine M;
+        memset(&M, 0, sizeof(M));
+        M.rng = ((unsigned long long)c->o.seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);   // java.util.Random(seed)
+        M.first_time = 1;
+        M.rowPerm = c->rl_rowPerm; M.cache_epoch = c->rl_epoch; M.cache_list = c->rl_clist;
+        M.list_off = c->rl_loff; M.list_cnt = c->rl_lcnt; M.list_me = c->rl_lme; M.tiepool = c->rl_tie; M.mymin = c->rl_mymin;
+        M.max_lists = c->rl_max_lists; M.tie_cap = c->rl_tie_cap; M.mymin_cap = c->rl_mymin_cap;
+        M.additive = c->o.additive ? 1 : 0;
+        M.cx_pos = M.cy_pos = -1;
+        FNN_CUDA(cudaMemsetAsync(c->rl_epoch, 0, sizeof(int) * n, c->stream));
+        FNN_CUDA(cudaMemcpyAsync(c->rl_machine, &M, sizeof(M), cudaMemcpyHostToDevice, c->stream));
+        FNN_CUDA(cudaStreamSynchronize(c->stream));
     }
     if (c->o.profile_every > 0) {
         // sampled per-launch timing of the selection kernel (roofline.achieved in bench.py)
@@ -1405,6 +1226,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     FNN_CUDA(cudaEventRecord(e1, c->stream));
     FNN_CUDA(cudaStreamSynchronize(c->stream));
     FNN_CUDA(cudaGetLastError());
+    if (c->h_st->error) { fnn::set_error("device-side selection strategy failed (code %d: 11/13 = tie or list pool overflow, 12 = candidate pool overflow, 10 = no pair found)", c->h_st->error); return FNN_E_STATE; }
     if (!c->h_st->done) { fnn::set_error("agglomeration did not terminate (m=%d after %d iterations)", c->h_st->m, c->h_st->iter); return FNN_E_STATE; }
     const int n_amalg = c->h_st->n_amalg;
     std::vector<int> lg(5 * (size_t)std::max(n_amalg, 1));

@@ -395,7 +395,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
                 st->selQ = bq;
                 st->sel_i = (int)(bk >> 32);
                 st->sel_j = (int)(bk & 0xffffffffu);
-                if (fused_select) select_body(ids, p2s, st, nullptr, nullptr);   // Cx, Cy, id-order swap: saves a launch
+                if (fused_select) select_body(ids, p2s, st, nullptr);   // Cx, Cy, id-order swap: saves a launch
             }
         }
     }
