@@ -1,13 +1,12 @@
 // fnn_modes.cuh — the Relaxed and Random selection strategies on the device.
 // Included by fnn_order.cu inside its anonymous namespace (needs DevState).
 //
-//   Random  (NeighborNetRandom.java:31-48, :130-178): fully device-resident.  One lane replays the
-//           reference's java.util.Random walk (the draw sequence is inherently serial: each bound
-//           depends on the node reached by the previous draw), the block evaluates the sampled Q
-//           values in parallel and reduces on (Q, draw index) = "first strict minimum in draw order".
-//   Relaxed (NeighborNetLocal.java:88-126): k_rowmin scans one node's row over ALL active nodes in
-//           position order and returns the minimum and every exact tie; the sampling / mutual-
-//           nearest logic of :170-264 is control flow and runs on the host (fnn_order.cu).
+//   Random  (NeighborNetRandom.java:31-48, :130-178): k_random_walk generates the reference's
+//           java.util.Random walk in parallel by speculation, k_random_eval evaluates the sampled Q
+//           values on all SMs and reduces on (Q, draw index) = "first strict minimum in draw order".
+//   Relaxed (NeighborNetLocal.java:88-264): k_relaxed_select - one lane runs the control flow as a
+//           resumable state machine (fnn_relaxed_sm.h), the block does the row scans (findRowMin,
+//           :88-126) and the -additive look-ahead (:280-466) it asks for.
 #pragma once
 #include "fnn_relaxed_sm.h"
 

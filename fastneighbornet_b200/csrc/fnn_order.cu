@@ -66,7 +66,7 @@ struct DevState {
     int chg_src[MAXK];
     double chg_Sx[MAXK];
     int final3[4];
-    // mode-specific selection (Relaxed: written by the host; Random: by k_random_select)
+    // mode-specific selection (Relaxed: written by k_relaxed_select; Random: by k_random_eval)
     int mode, mult, fallback, cx_pos, cy_pos;
     int rank, world;
     long long run_tag;            // (run counter << 32): makes mailbox tags unique across runs of one context
