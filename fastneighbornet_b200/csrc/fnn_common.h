@@ -10,6 +10,18 @@ void set_error(const char* fmt, ...);
 const char* last_error();
 }  // namespace fnn
 
+// frees a handful of cudaMalloc'ed scratch buffers on every exit path of a C-ABI entry point
+struct DevScratch {
+    void* ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int count = 0;
+    cudaError_t alloc(void** out, size_t bytes) {
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e == cudaSuccess && count < 8) ptr[count++] = *out;
+        return e;
+    }
+    ~DevScratch() { for (int i = 0; i < count; ++i) cudaFree(ptr[i]); }
+};
+
 // internal accessors across translation units (not part of the ABI)
 int64_t fnn_ctx_n_(fnn_ctx* c);
 void fnn_ctx_mark_loaded_(fnn_ctx* c);

@@ -162,16 +162,16 @@ extern "C" int fnn_ctx_synth(fnn_ctx* c, const double* h, const double* a, const
     for (int64_t i = 0; i < n; ++i) slot[i] = (int)slot_of_taxon[i];
     double *d_tab = nullptr, *d_a = nullptr;
     int* d_slot = nullptr;
-    FNN_CUDA(cudaMalloc((void**)&d_tab, tab.size() * sizeof(double)));
-    FNN_CUDA(cudaMalloc((void**)&d_a, n * sizeof(double)));
-    FNN_CUDA(cudaMalloc((void**)&d_slot, n * sizeof(int)));
+    DevScratch scratch;   // freed on every exit path
+    FNN_CUDA(scratch.alloc((void**)&d_tab, tab.size() * sizeof(double)));
+    FNN_CUDA(scratch.alloc((void**)&d_a, n * sizeof(double)));
+    FNN_CUDA(scratch.alloc((void**)&d_slot, n * sizeof(int)));
     FNN_CUDA(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     FNN_CUDA(cudaMemcpy(d_a, a, n * sizeof(double), cudaMemcpyHostToDevice));
     FNN_CUDA(cudaMemcpy(d_slot, slot.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     k_synth<<<148 * 8, 256>>>(dD, ld, (int)n, d_tab, d_a, d_slot, noise_base, eps);
     FNN_CUDA(cudaGetLastError());
     FNN_CUDA(cudaDeviceSynchronize());
-    cudaFree(d_tab); cudaFree(d_a); cudaFree(d_slot);
     fnn_ctx_mark_loaded_(c);
     return FNN_OK;
 }

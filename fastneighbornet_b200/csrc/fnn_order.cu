@@ -1289,8 +1289,9 @@ extern "C" int fnn_seq_sum(const fnn_opts* o, const double* rows, int32_t nrows,
     int rc = ensure_device(o);
     if (rc) return rc;
     double *d_rows = nullptr, *d_out = nullptr;
-    FNN_CUDA(cudaMalloc((void**)&d_rows, sizeof(double) * (size_t)nrows * (size_t)std::max<int64_t>(len, 1)));
-    FNN_CUDA(cudaMalloc((void**)&d_out, sizeof(double) * 4));
+    DevScratch scratch;   // freed on every exit path
+    FNN_CUDA(scratch.alloc((void**)&d_rows, sizeof(double) * (size_t)nrows * (size_t)std::max<int64_t>(len, 1)));
+    FNN_CUDA(scratch.alloc((void**)&d_out, sizeof(double) * 4));
     FNN_CUDA(cudaMemcpy(d_rows, rows, sizeof(double) * (size_t)nrows * (size_t)len, cudaMemcpyHostToDevice));
     FNN_CUDA(cudaFuncSetAttribute(k_seqsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICK_SMEM));
     k_seqsum<<<1, PICK_THREADS, PICK_SMEM>>>(d_rows, len, nrows, (int)len, d_out, o ? o->reserved[1] : 0);
@@ -1310,7 +1311,6 @@ extern "C" int fnn_seq_sum(const fnn_opts* o, const double* rows, int32_t nrows,
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
     FNN_CUDA(cudaMemcpy(out, d_out, sizeof(double) * nrows, cudaMemcpyDeviceToHost));
-    cudaFree(d_rows); cudaFree(d_out);
     return FNN_OK;
 }
 
