@@ -297,7 +297,7 @@ def main():
                     roofline["traffic"] = json.load(f).get("traffic_bytes_per_launch")
             except Exception:
                 pass
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N=1 only
             threads = host_threads()
             dt, b = cpu_reference_run(args.ref_n, 1, threads)
             cpu_baseline = {"value": b / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
