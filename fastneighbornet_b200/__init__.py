@@ -21,5 +21,6 @@ from .api import (  # noqa: F401
     split_weights,
     csw_matvec,
     weighted_splits,
+    network_splits,
 )
 from . import synth  # noqa: F401

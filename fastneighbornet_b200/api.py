@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "fnn_default_opts", "fnn_last_error", "fnn_device_count", "fnn_ctx_create", "fnn_ctx_destroy",
     "fnn_ctx_load_host", "fnn_ctx_load_device", "fnn_ctx_synth", "fnn_ctx_read_matrix", "fnn_ctx_order",
     "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums", "fnn_seq_sum",
-    "fnn_split_weights", "fnn_csw_matvec", "fnn_ctx_ipc_handle", "fnn_ctx_connect",
+    "fnn_split_weights", "fnn_csw_matvec", "fnn_ctx_ipc_handle", "fnn_ctx_connect", "fnn_weighted_splits",
 ]
 
 
@@ -98,6 +98,9 @@ def lib():
         L.fnn_rowsums.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int64, c_dp]
         L.fnn_split_weights.argtypes = [ctypes.POINTER(fnn_opts), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64, c_dp,
                                         ctypes.POINTER(ctypes.c_int64)]
+        L.fnn_weighted_splits.argtypes = [ctypes.POINTER(fnn_opts), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64, ctypes.c_double,
+                                          ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64,
+                                          ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
         L.fnn_csw_matvec.argtypes = [ctypes.POINTER(fnn_opts), ctypes.c_int32, c_dp, ctypes.c_int64, c_dp]
         L.fnn_seq_sum.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int32, ctypes.c_int64, c_dp]
         _LIB = L
@@ -264,6 +267,24 @@ def split_weights(ordering, d_upper, constrained=True, **opts):
     _check(lib().fnn_split_weights(ctypes.byref(o), ordering.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _dp(d_upper), n,
                                    _dp(x), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
     return x, {"cg_iters": int(st[0]), "cg_calls": int(st[1]), "outer": int(st[2]), "inner": int(st[3]), "kernel_launches": int(st[4])}
+
+
+def network_splits(ordering, d_upper, cutoff=1e-6, constrained=True, **opts):
+    """fnn_weighted_splits: solve and emit only the kept splits, compacted on the device.
+    Returns (split_i, split_j, weight) arrays; split k is the taxon set {ordering[split_i[k]+1 .. split_j[k]]}."""
+    ordering = np.ascontiguousarray(ordering, dtype=np.int32)
+    n = ordering.shape[0] - 1
+    d_upper = np.ascontiguousarray(d_upper, dtype=np.float64)
+    o = default_opts(**opts)
+    o.reserved[3] = 0 if constrained else 1
+    cap = n * (n - 1) // 2
+    si, sj, w = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.float64)
+    kept = ctypes.c_int64()
+    ip = ctypes.POINTER(ctypes.c_int32)
+    _check(lib().fnn_weighted_splits(ctypes.byref(o), ordering.ctypes.data_as(ip), _dp(d_upper), n, float(cutoff),
+                                     si.ctypes.data_as(ip), sj.ctypes.data_as(ip), _dp(w), cap, ctypes.byref(kept), None))
+    k = kept.value
+    return si[:k].copy(), sj[:k].copy(), w[:k].copy()
 
 
 def csw_matvec(which, v, n, **opts):

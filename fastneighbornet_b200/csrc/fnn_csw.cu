@@ -657,33 +657,100 @@ extern "C" int fnn_csw_matvec(const fnn_opts* o, int32_t which, const double* v,
     return rc;
 }
 
-extern "C" int fnn_split_weights(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double* x_out,
-                                 int64_t* stats_out) {
-    if (!ordering || !d_upper || !x_out || n < 4 || n > 20000) { fnn::set_error("fnn_split_weights: bad arguments (4 <= n <= 20000)"); return FNN_E_ARG; }
+// shared driver of the two B2 entry points: upload, permute to circular-position order, solve; leaves x on the device
+static int solve_split_weights(Csw& c, const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n) {
+    c.n = (int)n; c.np = n * (n - 1) / 2; c.nblk = (c.np + 1023) / 1024;
+    int rc = c.alloc();
+    if (rc) return rc;
+    int* d_ord = reinterpret_cast<int*>(c.tie_rank);   // scratch: free until the first 60 % collapse
+    FNN_CUDA(cudaMemcpyAsync(d_ord, ordering, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c.st));
+    FNN_CUDA(cudaMemcpyAsync(c.r, d_upper, sizeof(double) * c.np, cudaMemcpyHostToDevice, c.st));   // r as staging
+    k_setup_d<<<c.grid_rows(), 256, 0, c.st>>>(c.r, d_ord, c.d, c.n);
+    const bool unconstrained = o && o->reserved[3] == 1;
+    if (unconstrained) k_unconstrained<<<c.grid_rows(), 256, 0, c.st>>>(c.d, c.x, c.n);
+    else rc = active_conjugate(c);
+    return rc;
+}
+
+static int check_b2_args(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n) {
+    if (!ordering || !d_upper || n < 4 || n > 20000) { fnn::set_error("split weights: bad arguments (4 <= n <= 20000)"); return FNN_E_ARG; }
     int cnt = 0;
     if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) { cudaGetLastError(); fnn::set_error("no CUDA device available (libfastnn has no CPU fallback)"); return FNN_E_NODEVICE; }
     FNN_CUDA(cudaSetDevice(o ? o->device : 0));
+    return FNN_OK;
+}
+
+static int fetch_stats(Csw& c, int64_t* stats_out) {
+    FNN_CUDA(cudaMemcpyAsync(c.h_sc, c.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c.st));
+    FNN_CUDA(cudaStreamSynchronize(c.st));
+    FNN_CUDA(cudaGetLastError());
+    if (stats_out) { stats_out[0] = c.h_sc->iters_total; stats_out[1] = c.cg_calls; stats_out[2] = c.outer; stats_out[3] = c.inner; stats_out[4] = c.launches; }
+    return FNN_OK;
+}
+
+extern "C" int fnn_split_weights(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double* x_out,
+                                 int64_t* stats_out) {
+    int rc = check_b2_args(o, ordering, d_upper, n);
+    if (rc) return rc;
+    if (!x_out) { fnn::set_error("fnn_split_weights: null output"); return FNN_E_ARG; }
     Csw c;
-    c.n = (int)n; c.np = n * (n - 1) / 2; c.nblk = (c.np + 1023) / 1024;
-    int rc = c.alloc();
-    int* d_ord = nullptr;
-    if (!rc) {
-        FNN_CUDA(cudaMalloc((void**)&d_ord, sizeof(int) * (n + 1)));
-        FNN_CUDA(cudaMemcpyAsync(d_ord, ordering, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c.st));
-        FNN_CUDA(cudaMemcpyAsync(c.r, d_upper, sizeof(double) * c.np, cudaMemcpyHostToDevice, c.st));   // r as staging
-        k_setup_d<<<c.grid_rows(), 256, 0, c.st>>>(c.r, d_ord, c.d, c.n);
-        const bool unconstrained = o && o->reserved[3] == 1;
-        if (unconstrained) k_unconstrained<<<c.grid_rows(), 256, 0, c.st>>>(c.d, c.x, c.n);
-        else rc = active_conjugate(c);
-        if (!rc) {
-            FNN_CUDA(cudaMemcpyAsync(x_out, c.x, sizeof(double) * c.np, cudaMemcpyDeviceToHost, c.st));
-            FNN_CUDA(cudaMemcpyAsync(c.h_sc, c.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c.st));
-            FNN_CUDA(cudaStreamSynchronize(c.st));
-            FNN_CUDA(cudaGetLastError());
-            if (stats_out) { stats_out[0] = c.h_sc->iters_total; stats_out[1] = c.cg_calls; stats_out[2] = c.outer; stats_out[3] = c.inner; stats_out[4] = c.launches; }
-        }
+    rc = solve_split_weights(c, o, ordering, d_upper, n);
+    if (!rc && cudaMemcpyAsync(x_out, c.x, sizeof(double) * c.np, cudaMemcpyDeviceToHost, c.st) != cudaSuccess) {
+        fnn::set_error("fnn_split_weights: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = FNN_E_CUDA;
     }
-    if (d_ord) cudaFree(d_ord);
+    if (!rc) rc = fetch_stats(c, stats_out);
+    c.release();
+    return rc;
+}
+
+// (:94-108 / FastNN.java:455-466) keep x > cutoff, in (i,j) row-major-upper order - compacted on the device so that only
+// the ~3.7 n surviving splits cross PCIe instead of n(n-1)/2 weights
+__global__ void k_flag_above(const double* __restrict__ x, int* __restrict__ flag, int64_t len, double cutoff) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) flag[i] = x[i] > cutoff;
+}
+__global__ void k_gather(const double* __restrict__ x, const int* __restrict__ idx, double* __restrict__ out, int count) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = x[idx[i]];
+}
+
+extern "C" int fnn_weighted_splits(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double cutoff,
+                                   int32_t* split_i, int32_t* split_j, double* weight, int64_t max_out, int64_t* n_out,
+                                   int64_t* stats_out) {
+    int rc = check_b2_args(o, ordering, d_upper, n);
+    if (rc) return rc;
+    if (!split_i || !split_j || !weight || !n_out || max_out < 0) { fnn::set_error("fnn_weighted_splits: null output"); return FNN_E_ARG; }
+    Csw c;
+    rc = solve_split_weights(c, o, ordering, d_upper, n);
+    if (!rc) {
+        rc = [&]() -> int {
+            k_flag_above<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.tie_flag, c.np, cutoff);
+            cub::CountingInputIterator<int> idx(0);
+            size_t need = 0;
+            FNN_CUDA(cub::DeviceSelect::Flagged(nullptr, need, idx, c.tie_flag, c.tie_rank, c.d_count, (int)c.np, c.st));
+            if (c.ensure_tmp(need)) return FNN_E_CUDA;
+            FNN_CUDA(cub::DeviceSelect::Flagged(c.tmp, need, idx, c.tie_flag, c.tie_rank, c.d_count, (int)c.np, c.st));
+            int kept = 0;
+            FNN_CUDA(cudaMemcpyAsync(&kept, c.d_count, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+            FNN_CUDA(cudaStreamSynchronize(c.st));
+            *n_out = kept;
+            if (kept > max_out) { fnn::set_error("fnn_weighted_splits: %d splits kept, room for %lld", kept, (long long)max_out); return FNN_E_ARG; }
+            if (kept > 0) {
+                k_gather<<<c.grid1d(kept, 256), 256, 0, c.st>>>(c.x, c.tie_rank, c.neg, kept);
+                std::vector<int> idx_h(kept);
+                FNN_CUDA(cudaMemcpyAsync(idx_h.data(), c.tie_rank, sizeof(int) * kept, cudaMemcpyDeviceToHost, c.st));
+                FNN_CUDA(cudaMemcpyAsync(weight, c.neg, sizeof(double) * kept, cudaMemcpyDeviceToHost, c.st));
+                FNN_CUDA(cudaStreamSynchronize(c.st));
+                int64_t i = 0;
+                for (int k = 0; k < kept; ++k) {   // packed index -> (i, j); indices are increasing, so i only moves forward
+                    while (row_start(n, i + 1) <= idx_h[k]) ++i;
+                    split_i[k] = (int32_t)i;
+                    split_j[k] = (int32_t)(idx_h[k] - row_start(n, i) + i + 1);
+                }
+            }
+            return FNN_OK;
+        }();
+    }
+    if (!rc) rc = fetch_stats(c, stats_out);
     c.release();
     return rc;
 }

@@ -126,6 +126,13 @@ int fnn_rowsums(const fnn_opts* o, const double* D_rowmajor, int64_t n, double* 
 int fnn_split_weights(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double* x_out,
                       int64_t* stats_out);
 
+/* B2 with the split emission of FastNN.java:455-466 folded in: solves as fnn_split_weights, keeps
+ * x > cutoff (the reference's optionThreshold is 1e-6) in (i,j) row-major-upper order, compacted on the device.  Entry k is
+ * the split {ordering[split_i[k]+1 .. split_j[k]]} with weight[k]; the host builds BitSets for these only (the live code
+ * materialises all n(n-1)/2 of them, FastNN.java:405-419).  *n_out = number kept; FNN_E_ARG if it exceeds max_out. */
+int fnn_weighted_splits(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double cutoff,
+                        int32_t* split_i, int32_t* split_j, double* weight, int64_t max_out, int64_t* n_out, int64_t* stats_out);
+
 /* single mat-vec / stencil of the split-weight solver on a packed npairs vector, for kernel parity tests:
  * which = 0: d = A b (calculateAb, CircularSplitWeights.java:643-731); 1: p = A^T d (calculateAtx, :603-633);
  * 2: unconstrained closed form (runUnconstrainedLS, :247-271) */

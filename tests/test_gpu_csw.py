@@ -86,3 +86,16 @@ def test_weighted_splits_emission(fnn):
     assert len(splits) == int((x > 1e-6).sum())
     # split (i,j) lists ordering[i+1..j]
     assert all(len(s) >= 1 and w > 1e-6 for s, w in splits)
+
+
+def test_device_compacted_split_emission(fnn):
+    """fnn_weighted_splits (N2): the kept splits compacted on the device equal the x > 1e-6 filter of FastNN.java:455-466."""
+    D, o, du = _problem(90, 6, 0.05)
+    x, _ = fnn.split_weights(o, du)
+    si, sj, w = fnn.network_splits(o, du)
+    n = 90
+    idx = si.astype(np.int64) * (2 * n - si - 3) // 2 + sj - 1
+    keep = np.nonzero(x > 1e-6)[0]
+    assert (idx == keep).all() and (w == x[keep]).all()
+    ref = fnn.weighted_splits(o, x)
+    assert [sorted(int(t) for t in o[i + 1: j + 1]) for i, j in zip(si, sj)] == [s for s, _ in ref]
