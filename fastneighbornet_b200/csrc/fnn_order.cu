@@ -84,6 +84,9 @@ struct Partial { double q; unsigned long long key; };
 // (Q, i, j) min-loc into slot [iteration parity][rank] of EVERY peer's mailbox with plain stores over
 // NVLink (peer memory mapped through CUDA IPC); the tag carries the iteration number.
 constexpr int MAX_WORLD = 8;
+// below this many active nodes a full scan costs less than the cross-GPU exchange: every rank scans everything itself
+constexpr int SHARD_MIN_ACTIVE = 4096;
+__device__ __forceinline__ int effective_world(int world, int m) { return m > SHARD_MIN_ACTIVE ? world : 1; }
 // two 16-byte halves, each written with ONE vector store and carrying the tag, so no fence is needed between the
 // payload and the tag: a half is either entirely old or entirely new
 struct __align__(16) MailSlot { double q; long long tag0; unsigned long long key; long long tag1; };
@@ -426,7 +429,7 @@ __device__ void select_body(const int* __restrict__ id, const int* __restrict__ 
     const int m = st->m, P2 = st->P2;
     if (m == 4 && st->c == 2) { st->need_rx = 0; return; }   // special case is handled by k_pick
     const bool strategy = (st->mode != 0 && m > st->fallback);
-    if (st->world > 1 && !strategy) {
+    if (effective_world(st->world, m) > 1 && !strategy) {
         const int par = st->iter & 1;
         double bq = INFINITY;
         unsigned long long bk = ~0ull;

@@ -210,6 +210,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
     const int m = st->m, P2 = st->P2;
     const double cm2 = (double)st->c - 2.0;
     const int tid = threadIdx.x;
+    const int ew = effective_world(st->world, m);   // ranks that share this scan (1: every rank scans all tiles)
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMERS / 32); }
@@ -228,7 +229,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
         if (tid == CONSUMERS) {
             int stage = 0;
             uint32_t phase = 0;
-            for (TileIter it(m, st->rank + st->world * blockIdx.x, st->world * gridDim.x); it.valid(); it.next()) {
+            for (TileIter it(m, (ew > 1 ? st->rank : 0) + ew * blockIdx.x, ew * gridDim.x); it.valid(); it.next()) {
                 int r0, cb0;
                 it.decode(r0, cb0);
                 const int rEnd = min(r0 + TILE_ROWS, m);
@@ -252,7 +253,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
         const int box = gt >> 7, lc = (gt & 127) * 2;   // which box of the stage, local column
         const int uo = grp * RPG;                       // first chunk row of this group
         int tileParity = 0;
-        for (TileIter it(m, st->rank + st->world * blockIdx.x, st->world * gridDim.x); it.valid(); it.next(), tileParity ^= 1) {
+        for (TileIter it(m, (ew > 1 ? st->rank : 0) + ew * blockIdx.x, ew * gridDim.x); it.valid(); it.next(), tileParity ^= 1) {
             int r0, cb0;
             it.decode(r0, cb0);
             const int rEnd = min(r0 + TILE_ROWS, m);
@@ -381,7 +382,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
             for (int w = 1; w < THREADS / 32; ++w)
                 if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
             st->ticket = 0;
-            if (st->world > 1) {
+            if (ew > 1) {
                 // post this rank's partial into every rank's mailbox (own included); k_select merges
                 const int par = st->iter & 1;
                 const long long tag = st->run_tag + (long long)st->iter + 1;

@@ -10,7 +10,8 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ok = True
 quick = "--quick" in sys.argv
-cases = [("tree1500", tree_matrix(1500, 3, 0.05)), ("int700", integer_matrix(700, 2))]
+cases = [("tree1500", tree_matrix(1500, 3, 0.05)), ("int700", integer_matrix(700, 2)),
+         ("tree6000", tree_matrix(6000, 4, 0.05))]   # > 4096 active nodes: the scan is really sharded there
 if not quick:
     cases.append(("tree4000", tree_matrix(4000, 5, 0.05)))
 for name, D in cases:
