@@ -24,6 +24,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -82,6 +87,55 @@ struct TraceRow {          // one per agglomeration iteration
 
 struct RowMin { int me, row; double value; };
 
+// A fixed pool like the reference's Executors.newFixedThreadPool (FastNN.java:291-295): workers persist across
+// iterations, so the timed CPU baseline pays a wake-up per slice, not a thread creation.
+struct SlicePool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    std::function<void(int)> job;
+    int generation = 0, pending = 0;
+    bool stop = false;
+    explicit SlicePool(int T) {
+        for (int t = 1; t < T; ++t)
+            workers.emplace_back([this, t] {
+                int seen = 0;
+                while (true) {
+                    std::function<void(int)> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv_go.wait(lk, [&] { return stop || generation != seen; });
+                        if (stop) return;
+                        seen = generation;
+                        f = job;
+                    }
+                    f(t);
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        if (--pending == 0) cv_done.notify_one();
+                    }
+                }
+            });
+    }
+    void run(const std::function<void(int)>& f) {   // slices 1..T-1 on the workers, slice 0 here
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = f;
+            pending = (int)workers.size();
+            ++generation;
+        }
+        cv_go.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~SlicePool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_go.notify_all();
+        for (auto& w : workers) w.join();
+    }
+};
+
 struct Engine {
     int64_t n;
     double* D;             // n*n row-major, mutated in place like the Java double[][]
@@ -103,6 +157,7 @@ struct Engine {
     int64_t pair_evals = 0;
     double alg_bytes = 0.0;      // sum over canonical scans of 8 B per cross-cluster entry
     int threads = 1;             // >1: NeighborNetCanonical's thread-pool partition (NeighborNetCanonical.java:180-206)
+    std::unique_ptr<SlicePool> pool;
     std::vector<TraceRow>* trace = nullptr;
     int status = 0;
 
@@ -192,10 +247,8 @@ struct Engine {
             }
             bx[t] = lx; by[t] = ly; bb[t] = lb;
         };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < T; ++t) pool.emplace_back(slice, t);
-        slice(0);
-        for (auto& th : pool) th.join();
+        if (!pool) pool.reset(new SlicePool(T));
+        pool->run(slice);
         for (int t = 0; t < T; ++t)
             if (bx[t] >= 0 && (Cx < 0 || bb[t] < best)) { Cx = bx[t]; Cy = by[t]; best = bb[t]; }
     }
