@@ -283,7 +283,7 @@ def main():
         pctx.close()
         peak, peak_src = measured_peak()
         achieved = ps["prof_scan_bytes"] / (ps["prof_scan_ms"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_scan_tma", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        roofline = {"bound": "hbm", "kernel": "k_scan_tma", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                     "traffic": None, "peak_source": peak_src, "samples": ps["prof_scan_samples"],
                     "avg_launch_ms": ps["prof_scan_ms"] / max(1, ps["prof_scan_samples"]),
                     "alg_bytes_per_launch": ps["prof_scan_bytes"] / max(1, ps["prof_scan_samples"]),
@@ -302,6 +302,10 @@ def main():
             dt, b = cpu_reference_run(args.ref_n, 1, threads)
             cpu_baseline = {"value": b / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"one canonical ordering at n={args.ref_n} (same generator), {dt:.1f} s on {threads} threads"}
+            n1 = min(args.ref_n, 1500)   # the reference's -threads 1 figure on a smaller sample
+            dt1, b1 = cpu_reference_run(n1, 1, 1)
+            cpu_baseline["value_1thread"] = b1 / dt1 / 1e9
+            cpu_baseline["sample_1thread"] = f"n={n1}, {dt1:.1f} s on 1 thread"
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
