@@ -22,5 +22,6 @@ from .api import (  # noqa: F401
     csw_matvec,
     weighted_splits,
     network_splits,
+    network,
 )
 from . import synth  # noqa: F401

@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "fnn_default_opts", "fnn_last_error", "fnn_device_count", "fnn_ctx_create", "fnn_ctx_destroy",
     "fnn_ctx_load_host", "fnn_ctx_load_device", "fnn_ctx_synth", "fnn_ctx_read_matrix", "fnn_ctx_order",
     "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums", "fnn_seq_sum",
-    "fnn_split_weights", "fnn_csw_matvec", "fnn_ctx_ipc_handle", "fnn_ctx_connect", "fnn_weighted_splits",
+    "fnn_split_weights", "fnn_csw_matvec", "fnn_ctx_ipc_handle", "fnn_ctx_connect", "fnn_weighted_splits", "fnn_network",
 ]
 
 
@@ -101,6 +101,9 @@ def lib():
         L.fnn_weighted_splits.argtypes = [ctypes.POINTER(fnn_opts), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64, ctypes.c_double,
                                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64,
                                           ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+        L.fnn_network.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int64, ctypes.c_double, ctypes.POINTER(ctypes.c_int32),
+                                  ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64,
+                                  ctypes.POINTER(ctypes.c_int64)]
         L.fnn_csw_matvec.argtypes = [ctypes.POINTER(fnn_opts), ctypes.c_int32, c_dp, ctypes.c_int64, c_dp]
         L.fnn_seq_sum.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int32, ctypes.c_int64, c_dp]
         _LIB = L
@@ -285,6 +288,23 @@ def network_splits(ordering, d_upper, cutoff=1e-6, constrained=True, **opts):
                                      si.ctypes.data_as(ip), sj.ctypes.data_as(ip), _dp(w), cap, ctypes.byref(kept), None))
     k = kept.value
     return si[:k].copy(), sj[:k].copy(), w[:k].copy()
+
+
+def network(D, cutoff=1e-6, **opts):
+    """fnn_network: ordering + split weights + split emission in one call, distances kept on the device.
+    Returns (ordering, split_i, split_j, weight)."""
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    n = D.shape[0]
+    o = default_opts(**opts)
+    cap = n * (n - 1) // 2
+    ordering = np.zeros(n + 1, dtype=np.int32)
+    si, sj, w = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.float64)
+    kept = ctypes.c_int64()
+    ip = ctypes.POINTER(ctypes.c_int32)
+    _check(lib().fnn_network(ctypes.byref(o), _dp(D), n, float(cutoff), ordering.ctypes.data_as(ip), si.ctypes.data_as(ip),
+                             sj.ctypes.data_as(ip), _dp(w), cap, ctypes.byref(kept)))
+    k = kept.value
+    return ordering, si[:k].copy(), sj[:k].copy(), w[:k].copy()
 
 
 def csw_matvec(which, v, n, **opts):

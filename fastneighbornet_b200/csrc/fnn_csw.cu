@@ -658,13 +658,15 @@ extern "C" int fnn_csw_matvec(const fnn_opts* o, int32_t which, const double* v,
 }
 
 // shared driver of the two B2 entry points: upload, permute to circular-position order, solve; leaves x on the device
-static int solve_split_weights(Csw& c, const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n) {
+static int solve_split_weights(Csw& c, const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n,
+                               bool d_upper_on_device = false) {
     c.n = (int)n; c.np = n * (n - 1) / 2; c.nblk = (c.np + 1023) / 1024;
     int rc = c.alloc();
     if (rc) return rc;
     int* d_ord = reinterpret_cast<int*>(c.tie_rank);   // scratch: free until the first 60 % collapse
     FNN_CUDA(cudaMemcpyAsync(d_ord, ordering, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c.st));
-    FNN_CUDA(cudaMemcpyAsync(c.r, d_upper, sizeof(double) * c.np, cudaMemcpyHostToDevice, c.st));   // r as staging
+    FNN_CUDA(cudaMemcpyAsync(c.r, d_upper, sizeof(double) * c.np, d_upper_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             c.st));   // r as staging
     k_setup_d<<<c.grid_rows(), 256, 0, c.st>>>(c.r, d_ord, c.d, c.n);
     const bool unconstrained = o && o->reserved[3] == 1;
     if (unconstrained) k_unconstrained<<<c.grid_rows(), 256, 0, c.st>>>(c.d, c.x, c.n);
@@ -713,6 +715,36 @@ __global__ void k_gather(const double* __restrict__ x, const int* __restrict__ i
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = x[idx[i]];
 }
 
+// FastNN.java:455-466 on the device: keep the splits whose weight exceeds `cutoff`, compacted in (i, j) order.
+static int emit_kept_splits(Csw& c, int64_t n, double cutoff, int32_t* split_i, int32_t* split_j, double* weight, int64_t max_out,
+                            int64_t* n_out) {
+    k_flag_above<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.tie_flag, c.np, cutoff);
+    cub::CountingInputIterator<int> idx(0);
+    size_t need = 0;
+    FNN_CUDA(cub::DeviceSelect::Flagged(nullptr, need, idx, c.tie_flag, c.tie_rank, c.d_count, (int)c.np, c.st));
+    if (c.ensure_tmp(need)) return FNN_E_CUDA;
+    FNN_CUDA(cub::DeviceSelect::Flagged(c.tmp, need, idx, c.tie_flag, c.tie_rank, c.d_count, (int)c.np, c.st));
+    int kept = 0;
+    FNN_CUDA(cudaMemcpyAsync(&kept, c.d_count, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+    FNN_CUDA(cudaStreamSynchronize(c.st));
+    *n_out = kept;
+    if (kept > max_out) { fnn::set_error("weighted splits: %d splits kept, room for %lld", kept, (long long)max_out); return FNN_E_ARG; }
+    if (kept > 0) {
+        k_gather<<<c.grid1d(kept, 256), 256, 0, c.st>>>(c.x, c.tie_rank, c.neg, kept);
+        std::vector<int> idx_h(kept);
+        FNN_CUDA(cudaMemcpyAsync(idx_h.data(), c.tie_rank, sizeof(int) * kept, cudaMemcpyDeviceToHost, c.st));
+        FNN_CUDA(cudaMemcpyAsync(weight, c.neg, sizeof(double) * kept, cudaMemcpyDeviceToHost, c.st));
+        FNN_CUDA(cudaStreamSynchronize(c.st));
+        int64_t i = 0;
+        for (int k = 0; k < kept; ++k) {   // packed index -> (i, j); indices are increasing, so i only moves forward
+            while (row_start(n, i + 1) <= idx_h[k]) ++i;
+            split_i[k] = (int32_t)i;
+            split_j[k] = (int32_t)(idx_h[k] - row_start(n, i) + i + 1);
+        }
+    }
+    return FNN_OK;
+}
+
 extern "C" int fnn_weighted_splits(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double cutoff,
                                    int32_t* split_i, int32_t* split_j, double* weight, int64_t max_out, int64_t* n_out,
                                    int64_t* stats_out) {
@@ -722,35 +754,56 @@ extern "C" int fnn_weighted_splits(const fnn_opts* o, const int32_t* ordering, c
     Csw c;
     rc = solve_split_weights(c, o, ordering, d_upper, n);
     if (!rc) {
-        rc = [&]() -> int {
-            k_flag_above<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.tie_flag, c.np, cutoff);
-            cub::CountingInputIterator<int> idx(0);
-            size_t need = 0;
-            FNN_CUDA(cub::DeviceSelect::Flagged(nullptr, need, idx, c.tie_flag, c.tie_rank, c.d_count, (int)c.np, c.st));
-            if (c.ensure_tmp(need)) return FNN_E_CUDA;
-            FNN_CUDA(cub::DeviceSelect::Flagged(c.tmp, need, idx, c.tie_flag, c.tie_rank, c.d_count, (int)c.np, c.st));
-            int kept = 0;
-            FNN_CUDA(cudaMemcpyAsync(&kept, c.d_count, sizeof(int), cudaMemcpyDeviceToHost, c.st));
-            FNN_CUDA(cudaStreamSynchronize(c.st));
-            *n_out = kept;
-            if (kept > max_out) { fnn::set_error("fnn_weighted_splits: %d splits kept, room for %lld", kept, (long long)max_out); return FNN_E_ARG; }
-            if (kept > 0) {
-                k_gather<<<c.grid1d(kept, 256), 256, 0, c.st>>>(c.x, c.tie_rank, c.neg, kept);
-                std::vector<int> idx_h(kept);
-                FNN_CUDA(cudaMemcpyAsync(idx_h.data(), c.tie_rank, sizeof(int) * kept, cudaMemcpyDeviceToHost, c.st));
-                FNN_CUDA(cudaMemcpyAsync(weight, c.neg, sizeof(double) * kept, cudaMemcpyDeviceToHost, c.st));
-                FNN_CUDA(cudaStreamSynchronize(c.st));
-                int64_t i = 0;
-                for (int k = 0; k < kept; ++k) {   // packed index -> (i, j); indices are increasing, so i only moves forward
-                    while (row_start(n, i + 1) <= idx_h[k]) ++i;
-                    split_i[k] = (int32_t)i;
-                    split_j[k] = (int32_t)(idx_h[k] - row_start(n, i) + i + 1);
-                }
-            }
-            return FNN_OK;
-        }();
+        rc = emit_kept_splits(c, n, cutoff, split_i, split_j, weight, max_out, n_out);
     }
     if (!rc) rc = fetch_stats(c, stats_out);
     c.release();
+    return rc;
+}
+
+// packed upper triangle (DistancesAndNames order) of an n x ld device matrix
+__global__ void k_pack_upper(const double* __restrict__ D, int64_t ld, int n, double* __restrict__ out) {
+    const int i = blockIdx.y;
+    if (i > n - 2) return;
+    const int64_t rs = (int64_t)i * (2 * n - i - 1) / 2;
+    for (int j = i + 1 + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[rs + (j - i - 1)] = D[(int64_t)i * ld + j];
+}
+
+// The whole network in one call (SURVEY §8b "optional fnn_network"): FastNN.main's ordering stage and split stage chained
+// with the distances kept on the device - the packed upper triangle is taken from the device matrix before the ordering
+// consumes it, so the split stage uploads nothing but the ordering.
+extern "C" int fnn_network(const fnn_opts* o, const double* D_rowmajor, int64_t n, double cutoff, int32_t* ordering_out,
+                           int32_t* split_i, int32_t* split_j, double* weight, int64_t max_out, int64_t* n_out) {
+    if (!D_rowmajor || !ordering_out || !split_i || !split_j || !weight || !n_out || n < 4 || n > 20000) {
+        fnn::set_error("fnn_network: bad arguments (4 <= n <= 20000)");
+        return FNN_E_ARG;
+    }
+    fnn_ctx* ctx = nullptr;
+    int rc = fnn_ctx_create(o, n, &ctx);
+    if (rc) return rc;
+    double* d_upper = nullptr;
+    rc = [&]() -> int {
+        int r = fnn_ctx_load_host(ctx, D_rowmajor);
+        if (r) return r;
+        double* dD; int64_t ld;
+        fnn_ctx_matrix_ptr(ctx, &dD, &ld);
+        const int64_t np = n * (n - 1) / 2;
+        FNN_CUDA(cudaMalloc((void**)&d_upper, sizeof(double) * np));
+        k_pack_upper<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 64)), (unsigned)(n - 1)), 256>>>(dD, ld, (int)n, d_upper);
+        FNN_CUDA(cudaGetLastError());
+        FNN_CUDA(cudaDeviceSynchronize());
+        r = fnn_ctx_order(ctx, ordering_out);
+        return r;
+    }();
+    fnn_ctx_destroy(ctx);
+    if (!rc) {
+        Csw c;
+        rc = solve_split_weights(c, o, ordering_out, d_upper, n, true);
+        if (!rc) {
+            rc = emit_kept_splits(c, n, cutoff, split_i, split_j, weight, max_out, n_out);
+        }
+        c.release();
+    }
+    if (d_upper) cudaFree(d_upper);
     return rc;
 }

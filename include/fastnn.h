@@ -133,6 +133,12 @@ int fnn_split_weights(const fnn_opts* o, const int32_t* ordering, const double* 
 int fnn_weighted_splits(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double cutoff,
                         int32_t* split_i, int32_t* split_j, double* weight, int64_t max_out, int64_t* n_out, int64_t* stats_out);
 
+/* B1 + B2 chained with the distances kept on the device (FastNN.main without -order, FastNN.java:378-466): ordering, then
+ * split weights of the SAME matrix (its packed upper triangle is taken on the device before the ordering consumes it),
+ * then the kept splits as in fnn_weighted_splits.  D_rowmajor: host, n*n, symmetric, zero diagonal. */
+int fnn_network(const fnn_opts* o, const double* D_rowmajor, int64_t n, double cutoff, int32_t* ordering_out,
+                int32_t* split_i, int32_t* split_j, double* weight, int64_t max_out, int64_t* n_out);
+
 /* single mat-vec / stencil of the split-weight solver on a packed npairs vector, for kernel parity tests:
  * which = 0: d = A b (calculateAb, CircularSplitWeights.java:643-731); 1: p = A^T d (calculateAtx, :603-633);
  * 2: unconstrained closed form (runUnconstrainedLS, :247-271) */

@@ -99,3 +99,13 @@ def test_device_compacted_split_emission(fnn):
     assert (idx == keep).all() and (w == x[keep]).all()
     ref = fnn.weighted_splits(o, x)
     assert [sorted(int(t) for t in o[i + 1: j + 1]) for i, j in zip(si, sj)] == [s for s, _ in ref]
+
+
+def test_network_one_call(fnn):
+    """fnn_network = fnn_order followed by fnn_weighted_splits on the same matrix, distances kept on the device."""
+    D = tree_matrix(70, 8, 0.05)
+    o, si, sj, w = fnn.network(D)
+    o_ref = fnn.order(D)
+    s2 = fnn.network_splits(o_ref, synth.upper_triangle(D))
+    assert (o == o_ref).all()
+    assert (si == s2[0]).all() and (sj == s2[1]).all() and (w == s2[2]).all()
