@@ -109,3 +109,19 @@ def test_network_one_call(fnn):
     s2 = fnn.network_splits(o_ref, synth.upper_triangle(D))
     assert (o == o_ref).all()
     assert (si == s2[0]).all() and (sj == s2[1]).all() and (w == s2[2]).all()
+
+
+def test_network_recovers_circular_split_system(fnn):
+    """Known answer (consistency of Neighbor-Net on circular metrics): a metric built from strictly positive weights on all
+    circular splits of a cycle gives back that cycle and those weights."""
+    from helpers import canon_cycle, circular_metric, split_dict
+    n = 40
+    cyc, w, D, du = circular_metric(n, 5)
+    o, si, sj, wt = fnn.network(D, cutoff=0.0)
+    assert canon_cycle(o.tolist()) == canon_cycle(cyc)
+    x = np.zeros(n * (n - 1) // 2)
+    rs = lambda i: i * (2 * n - i - 1) // 2
+    for i, j, v in zip(si, sj, wt):
+        x[rs(i) + (j - i - 1)] = v
+    got, want = split_dict(n, o, x), split_dict(n, cyc, w)
+    assert max(abs(got[k] - want[k]) for k in want) < 1e-8

@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 from oracle import pyref
-from helpers import integer_matrix, random_matrix, tree_matrix
+from helpers import canon_cycle, circular_metric, integer_matrix, random_matrix, split_dict, tree_matrix
 from fastneighbornet_b200 import synth
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -163,3 +163,16 @@ def test_csw_additive_tree_reproduces_distances():
     D, o, du, d_pos = _csw_problem(n, 7, 0.0)
     x, _ = oracle.split_weights(n, d_pos)
     assert np.abs(oracle.ab(n, x) - d_pos).max() < 1e-9
+
+
+# ---- a published known answer: Neighbor-Net is consistent on circular metrics (Bryant, Moulton & Spillner 2007) ----
+@pytest.mark.parametrize("n,seed", [(8, 1), (13, 2), (24, 3)])
+def test_consistency_on_circular_metrics(n, seed):
+    cyc, w, D, du = circular_metric(n, seed)
+    o, _, _ = oracle.order(D)
+    assert canon_cycle(o.tolist()) == canon_cycle(cyc)                # (a)+(b): the generating cycle is recovered
+    assert canon_cycle(_py(D, "canonical", 0, 1024)[0].tolist()) == canon_cycle(cyc)
+    x, _ = oracle.split_weights(n, oracle.setup_d(o, du))               # (c): and so are the generating weights
+    got, want = split_dict(n, o, x), split_dict(n, cyc, w)
+    assert got.keys() == want.keys()
+    assert max(abs(got[k] - want[k]) for k in want) < 1e-8
