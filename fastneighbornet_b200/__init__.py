@@ -23,5 +23,6 @@ from .api import (  # noqa: F401
     weighted_splits,
     network_splits,
     network,
+    read_phylip,
 )
 from . import synth  # noqa: F401

@@ -60,6 +60,7 @@ ABI_SYMBOLS = [
     "fnn_ctx_load_host", "fnn_ctx_load_device", "fnn_ctx_synth", "fnn_ctx_read_matrix", "fnn_ctx_order",
     "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums", "fnn_seq_sum",
     "fnn_split_weights", "fnn_csw_matvec", "fnn_ctx_ipc_handle", "fnn_ctx_connect", "fnn_weighted_splits", "fnn_network",
+    "fnn_phylip_taxa", "fnn_read_phylip",
 ]
 
 
@@ -101,6 +102,8 @@ def lib():
         L.fnn_weighted_splits.argtypes = [ctypes.POINTER(fnn_opts), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64, ctypes.c_double,
                                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64,
                                           ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+        L.fnn_phylip_taxa.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]
+        L.fnn_read_phylip.argtypes = [ctypes.c_char_p, ctypes.c_int64, c_dp, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int]
         L.fnn_network.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int64, ctypes.c_double, ctypes.POINTER(ctypes.c_int32),
                                   ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64,
                                   ctypes.POINTER(ctypes.c_int64)]
@@ -288,6 +291,19 @@ def network_splits(ordering, d_upper, cutoff=1e-6, constrained=True, **opts):
                                      si.ctypes.data_as(ip), sj.ctypes.data_as(ip), _dp(w), cap, ctypes.byref(kept), None))
     k = kept.value
     return si[:k].copy(), sj[:k].copy(), w[:k].copy()
+
+
+def read_phylip(path, threads=0, name_len=64):
+    """Native Phylip loader (fnn_phylip_taxa + fnn_read_phylip; host only, no device needed).
+    Returns (D[n, n] float64, names list)."""
+    n = ctypes.c_int64()
+    _check(lib().fnn_phylip_taxa(str(path).encode(), ctypes.byref(n)))
+    n = n.value
+    D = np.empty((n, n), dtype=np.float64)
+    names = ctypes.create_string_buffer(n * name_len)
+    _check(lib().fnn_read_phylip(str(path).encode(), n, _dp(D), names, name_len, int(threads)))
+    raw = names.raw
+    return D, [raw[i * name_len:(i + 1) * name_len].split(b"\0", 1)[0].decode("ascii", "replace") for i in range(n)]
 
 
 def network(D, cutoff=1e-6, **opts):

@@ -1,5 +1,5 @@
-// fnn_host.cu — host-side pieces of libfastnn.so: error state, the one-shot B1 seam, the
-// native Phylip reader (conventions of DistancesAndNames.java:43-132), and the
+// fnn_host.cu — host-side pieces of libfastnn.so: error state, the one-shot B1 seam (its Phylip input goes through
+// csrc/fnn_phylip.cpp), and the
 // device generator for the synthetic additive-tree metrics.
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -23,70 +23,6 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 }  // namespace fnn
 
-// ---- Phylip: line 1 = n (all whitespace stripped, FastNN.java:272-274); then `name v v v ...`
-// split on single spaces, then tabs; only columns < row are consumed (DistancesAndNames.java:65-87),
-// so square and lower-triangular files both load.
-static int read_phylip(const char* path, int64_t n, std::vector<double>& D) {
-    FILE* f = fopen(path, "rb");
-    if (!f) { fnn::set_error("cannot open %s", path); return FNN_E_IO; }
-    std::string line;
-    auto getline_ = [&](std::string& out) -> bool {
-        out.clear();
-        int ch;
-        bool any = false;
-        while ((ch = fgetc(f)) != EOF) {
-            any = true;
-            if (ch == '\n') break;
-            out.push_back((char)ch);
-        }
-        if (!out.empty() && out.back() == '\r') out.pop_back();
-        return any;
-    };
-    if (!getline_(line)) { fclose(f); fnn::set_error("%s: empty file", path); return FNN_E_IO; }
-    std::string digits;
-    for (char ch : line) if (!isspace((unsigned char)ch)) digits.push_back(ch);
-    const long long n_file = atoll(digits.c_str());
-    if (n_file != n) { fclose(f); fnn::set_error("%s: header says %lld taxa, caller says %lld", path, n_file, (long long)n); return FNN_E_ARG; }
-    D.assign((size_t)n * n, 0.0);
-    int64_t row = 0;
-    std::vector<const char*> toks;
-    while (row < n && getline_(line)) {
-        // tokens: split on ' ' then '\t'; first token is the name
-        size_t p = 0;
-        bool first = true;
-        int64_t col = 0;
-        bool empty_name = false;
-        while (p <= line.size()) {
-            size_t e = line.find(' ', p);
-            if (e == std::string::npos) e = line.size();
-            if (first) {
-                first = false;
-                if (e == p && line.empty()) empty_name = true;
-            } else if (e > p) {
-                size_t q = p;
-                while (q < e) {
-                    size_t te = line.find('\t', q);
-                    if (te == std::string::npos || te > e) te = e;
-                    if (te > q && col < row) {
-                        const double v = strtod(line.substr(q, te - q).c_str(), nullptr);
-                        D[(size_t)row * n + col] = v;
-                        D[(size_t)col * n + row] = v;
-                        ++col;
-                    }
-                    q = te + 1;
-                }
-            }
-            p = e + 1;
-        }
-        if (empty_name) break;
-        if (col < row) { fclose(f); fnn::set_error("%s: row %lld has %lld of %lld lower-triangle values", path, (long long)row, (long long)col, (long long)row); return FNN_E_IO; }
-        ++row;
-    }
-    fclose(f);
-    if (row < n) { fnn::set_error("%s: %lld rows, expected %lld", path, (long long)row, (long long)n); return FNN_E_IO; }
-    return FNN_OK;
-}
-
 extern "C" int fnn_order(const fnn_opts* o, const double* Dh, const char* phylip_path, int64_t n, int32_t* ordering) {
     if (!ordering || n < 1 || ((Dh == nullptr) == (phylip_path == nullptr))) {
         fnn::set_error("fnn_order: need n>=1, ordering_out, and exactly one of D_rowmajor / phylip_path");
@@ -97,8 +33,9 @@ extern "C" int fnn_order(const fnn_opts* o, const double* Dh, const char* phylip
         return FNN_OK;
     }
     std::vector<double> file_D;
-    if (phylip_path) {
-        int rc = read_phylip(phylip_path, n, file_D);
+    if (phylip_path) {   // native loader, csrc/fnn_phylip.cpp
+        file_D.resize((size_t)n * n);
+        int rc = fnn_read_phylip(phylip_path, n, file_D.data(), nullptr, 0, 0);
         if (rc) return rc;
         Dh = file_D.data();
     }

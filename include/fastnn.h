@@ -133,6 +133,14 @@ int fnn_split_weights(const fnn_opts* o, const int32_t* ordering, const double* 
 int fnn_weighted_splits(const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n, double cutoff,
                         int32_t* split_i, int32_t* split_j, double* weight, int64_t max_out, int64_t* n_out, int64_t* stats_out);
 
+/* Native Phylip loader (host only, needs no device).  Replaces FastNN.java:270-276 (header) and
+ * DistancesAndNames.java:43-132 + FastNN.java:297-312 (rows -> packed triangle -> double[n][n]) with one multi-threaded
+ * pass over the mmap'ed file.  fnn_phylip_taxa: the taxon count of line 1.  fnn_read_phylip: D_rowmajor (n*n, symmetric,
+ * zero diagonal); names (optional) receives n NUL-terminated names, name_stride bytes apart (truncated to fit);
+ * threads 0 = all host cores.  Every value is the correctly rounded double of its token, as Double.valueOf gives. */
+int fnn_phylip_taxa(const char* phylip_path, int64_t* n_out);
+int fnn_read_phylip(const char* phylip_path, int64_t n, double* D_rowmajor, char* names, int64_t name_stride, int threads);
+
 /* B1 + B2 chained with the distances kept on the device (FastNN.main without -order, FastNN.java:378-466): ordering, then
  * split weights of the SAME matrix (its packed upper triangle is taken on the device before the ordering consumes it),
  * then the kept splits as in fnn_weighted_splits.  D_rowmajor: host, n*n, symmetric, zero diagonal. */
