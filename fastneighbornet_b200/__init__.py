@@ -24,5 +24,7 @@ from .api import (  # noqa: F401
     network_splits,
     network,
     read_phylip,
+    write_nexus,
+    java_double_str,
 )
 from . import synth  # noqa: F401

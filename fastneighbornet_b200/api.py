@@ -60,7 +60,7 @@ ABI_SYMBOLS = [
     "fnn_ctx_load_host", "fnn_ctx_load_device", "fnn_ctx_synth", "fnn_ctx_read_matrix", "fnn_ctx_order",
     "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums", "fnn_seq_sum",
     "fnn_split_weights", "fnn_csw_matvec", "fnn_ctx_ipc_handle", "fnn_ctx_connect", "fnn_weighted_splits", "fnn_network",
-    "fnn_phylip_taxa", "fnn_read_phylip",
+    "fnn_phylip_taxa", "fnn_read_phylip", "fnn_write_nexus", "fnn_java_double_to_string",
 ]
 
 
@@ -104,6 +104,10 @@ def lib():
                                           ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
         L.fnn_phylip_taxa.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]
         L.fnn_read_phylip.argtypes = [ctypes.c_char_p, ctypes.c_int64, c_dp, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int]
+        ip32 = ctypes.POINTER(ctypes.c_int32)
+        L.fnn_write_nexus.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int64, c_dp, ip32, ip32, ip32, c_dp,
+                                      ctypes.c_int64, ctypes.c_int]
+        L.fnn_java_double_to_string.argtypes = [ctypes.c_double, ctypes.c_char_p, ctypes.c_int64]
         L.fnn_network.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int64, ctypes.c_double, ctypes.POINTER(ctypes.c_int32),
                                   ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64,
                                   ctypes.POINTER(ctypes.c_int64)]
@@ -304,6 +308,34 @@ def read_phylip(path, threads=0, name_len=64):
     _check(lib().fnn_read_phylip(str(path).encode(), n, _dp(D), names, name_len, int(threads)))
     raw = names.raw
     return D, [raw[i * name_len:(i + 1) * name_len].split(b"\0", 1)[0].decode("ascii", "replace") for i in range(n)]
+
+
+def java_double_str(v):
+    """Double.toString(v) as the Nexus writer prints it."""
+    buf = ctypes.create_string_buffer(40)
+    _check(lib().fnn_java_double_to_string(float(v), buf, 40))
+    return buf.value.decode()
+
+
+def write_nexus(path, ordering, split_i, split_j, weight, D=None, names=None, threads=0):
+    """fnn_write_nexus: the output of OutputPrinter.NexusWithSplitsAndDistances for the kept splits (host only)."""
+    ordering = np.ascontiguousarray(ordering, dtype=np.int32)
+    n = ordering.shape[0] - 1
+    si = np.ascontiguousarray(split_i, dtype=np.int32)
+    sj = np.ascontiguousarray(split_j, dtype=np.int32)
+    w = np.ascontiguousarray(weight, dtype=np.float64)
+    ip = ctypes.POINTER(ctypes.c_int32)
+    nbuf, stride = None, 0
+    if names is not None:
+        enc = [str(s).encode("ascii", "replace") for s in names]
+        stride = max(len(e) for e in enc) + 1
+        nbuf = b"".join(e.ljust(stride, b"\0") for e in enc)
+    Dp = None
+    if D is not None:
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        Dp = _dp(D)
+    _check(lib().fnn_write_nexus(None if path is None else str(path).encode(), n, nbuf, stride, Dp, ordering.ctypes.data_as(ip),
+                                 si.ctypes.data_as(ip), sj.ctypes.data_as(ip), _dp(w), len(w), int(threads)))
 
 
 def network(D, cutoff=1e-6, **opts):

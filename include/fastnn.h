@@ -141,6 +141,17 @@ int fnn_weighted_splits(const fnn_opts* o, const int32_t* ordering, const double
 int fnn_phylip_taxa(const char* phylip_path, int64_t* n_out);
 int fnn_read_phylip(const char* phylip_path, int64_t n, double* D_rowmajor, char* names, int64_t name_stride, int threads);
 
+/* Streaming Nexus emission (host only).  Writes what OutputPrinter.NexusWithSplitsAndDistances prints
+ * (OutputPrinter.java:8-96) from the compact output of fnn_weighted_splits / fnn_network: split k is
+ * {ordering[split_i[k]+1 .. split_j[k]]} with weight[k]; member lists are generated while the line is written, no
+ * n(n-1)/2 BitSets (FastNN.java:405-419).  path NULL or "-" = stdout.  names NULL = t1..tn.  D_rowmajor NULL skips the
+ * Distances block (an extension: at n = 20 000 that block alone is ~6 GB of text).  Numbers are formatted like
+ * Double.toString (shortest round-trip digits, JDK >= 19); fnn_java_double_to_string exposes that formatter. */
+int fnn_write_nexus(const char* path, int64_t n, const char* names, int64_t name_stride, const double* D_rowmajor,
+                    const int32_t* ordering, const int32_t* split_i, const int32_t* split_j, const double* weight,
+                    int64_t n_splits, int threads);
+int fnn_java_double_to_string(double v, char* out, int64_t out_len);
+
 /* B1 + B2 chained with the distances kept on the device (FastNN.main without -order, FastNN.java:378-466): ordering, then
  * split weights of the SAME matrix (its packed upper triangle is taken on the device before the ordering consumes it),
  * then the kept splits as in fnn_weighted_splits.  D_rowmajor: host, n*n, symmetric, zero diagonal. */
