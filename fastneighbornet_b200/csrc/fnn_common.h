@@ -22,6 +22,14 @@ struct DevScratch {
     ~DevScratch() { for (int i = 0; i < count; ++i) cudaFree(ptr[i]); }
 };
 
+// a cudaEvent_t that is destroyed on every exit path
+struct DevEvent {
+    cudaEvent_t e = nullptr;
+    cudaError_t create() { return cudaEventCreate(&e); }
+    operator cudaEvent_t() const { return e; }
+    ~DevEvent() { if (e) cudaEventDestroy(e); }
+};
+
 // internal accessors across translation units (not part of the ABI)
 int64_t fnn_ctx_n_(fnn_ctx* c);
 void fnn_ctx_mark_loaded_(fnn_ctx* c);

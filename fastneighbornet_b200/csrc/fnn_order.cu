@@ -913,6 +913,8 @@ extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
     delete c;
 }
 
+static int ctx_build(fnn_ctx* c, const fnn_opts* o, int64_t n);
+
 extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     if (!out || n < 1) { fnn::set_error("fnn_ctx_create: bad arguments"); return FNN_E_ARG; }
     fnn_opts d;
@@ -925,6 +927,13 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     fnn_ctx* c = new fnn_ctx();
     c->o = *o;
     c->n = n;
+    rc = ctx_build(c, o, n);
+    if (rc) { fnn_ctx_destroy(c); return rc; }   // every failure path releases what was allocated so far
+    *out = c;
+    return FNN_OK;
+}
+
+static int ctx_build(fnn_ctx* c, const fnn_opts* o, int64_t n) {
     c->serial_chain = (o->reserved[1] == 1) || n > (int64_t)xsum::THREADS * xsum::LEAF_MAX;
     c->ld = (n + 15) / 16 * 16;
     cudaDeviceProp prop;
@@ -936,7 +945,6 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
         if (e_ != cudaSuccess) {                                                               \
             fnn::set_error("cudaMalloc(%zu bytes) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); \
             cudaGetLastError();                                                                \
-            fnn_ctx_destroy(c);                                                                \
             return FNN_E_NOMEM;                                                                \
         }                                                                                      \
     } while (0)
@@ -991,10 +999,9 @@ extern "C" int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out) {
     c->scan_grid = std::max(c->scan_grid, c->sms);
     if (o->reserved[0] == 0) {  // reserved[0] = 1 selects the register-tiled scan (A/B only)
         int trc = make_tensor_map(c);
-        if (trc) { fnn_ctx_destroy(c); return trc; }
+        if (trc) return trc;
         FNN_CUDA(cudaFuncSetAttribute(tma::k_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma::SMEM_BYTES));
     }
-    *out = c;
     return FNN_OK;
 }
 
@@ -1009,8 +1016,8 @@ static int after_load(fnn_ctx* c) {
 extern "C" int fnn_ctx_load_host(fnn_ctx* c, const double* Dh) {
     if (!c || !Dh) { fnn::set_error("fnn_ctx_load_host: null argument"); return FNN_E_ARG; }
     FNN_CUDA(cudaSetDevice(c->o.device));
-    cudaEvent_t e0, e1;
-    FNN_CUDA(cudaEventCreate(&e0)); FNN_CUDA(cudaEventCreate(&e1));
+    DevEvent e0, e1;
+    FNN_CUDA(e0.create()); FNN_CUDA(e1.create());
     FNN_CUDA(cudaEventRecord(e0, c->stream));
     FNN_CUDA(cudaMemcpy2DAsync(c->D, c->ld * sizeof(double), Dh, c->n * sizeof(double), c->n * sizeof(double), c->n,
                                cudaMemcpyHostToDevice, c->stream));
@@ -1020,7 +1027,6 @@ extern "C" int fnn_ctx_load_host(fnn_ctx* c, const double* Dh) {
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     c->stats.h2d_ms = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }
 
@@ -1098,7 +1104,7 @@ static inline void launch_rest(fnn_ctx* c) {
 
 
 // expandNodes (NetMakerOriginal.java:246-325) on the host from the amalgamation log
-static void expand_order(int64_t n, const std::vector<int>& lg, int n_amalg, const int* final3, int32_t* ordering) {
+static bool expand_order(int64_t n, const std::vector<int>& lg, int n_amalg, const int* final3, int32_t* ordering) {
     const int maxid = (int)n + 2 * n_amalg + 2;
     std::vector<int> ch1(maxid + 1, 0), ch2(maxid + 1, 0), nbr(maxid + 1, 0), nxt(maxid + 1, 0), prv(maxid + 1, 0);
     for (int k = 0; k < n_amalg; ++k) {
@@ -1119,10 +1125,14 @@ static void expand_order(int64_t n, const std::vector<int>& lg, int n_amalg, con
         nxt[y] = z; prv[z] = y;
         nxt[z] = nxt[v]; prv[nxt[z]] = z;
     }
-    while (x != 1) x = nxt[x];
+    for (int64_t guard = 0; x != 1; ++guard) {   // rotate to taxon 1 (:312-316); a damaged log must not spin forever
+        if (guard > n) return false;
+        x = nxt[x];
+    }
     int a = x, t = 0;
     ordering[0] = 0;
-    do { ordering[++t] = a; a = nxt[a]; } while (a != x && t <= n);
+    do { ordering[++t] = a; a = nxt[a]; } while (a != x && t < n);
+    return a == x && t == n;
 }
 
 extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
@@ -1135,8 +1145,8 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     if (!c->loaded) { fnn::set_error("fnn_ctx_order: no matrix loaded"); return FNN_E_STATE; }
     FNN_CUDA(cudaSetDevice(c->o.device));
     c->loaded = false;  // the matrix is consumed
-    cudaEvent_t e0, e1;
-    FNN_CUDA(cudaEventCreate(&e0)); FNN_CUDA(cudaEventCreate(&e1));
+    DevEvent e0, e1;
+    FNN_CUDA(e0.create()); FNN_CUDA(e1.create());
     FNN_CUDA(cudaEventRecord(e0, c->stream));
     const int ni = (int)n;
     k_init_nodes<<<(ni + 255) / 256, 256, 0, c->stream>>>(ni, c->id, c->pos, c->p2s, c->st, c->o.mode, c->o.mult,
@@ -1164,8 +1174,8 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     }
     if (c->o.profile_every > 0) {
         // sampled per-launch timing of the selection kernel (roofline.achieved in bench.py)
-        cudaEvent_t p0, p1;
-        FNN_CUDA(cudaEventCreate(&p0)); FNN_CUDA(cudaEventCreate(&p1));
+        DevEvent p0, p1;
+        FNN_CUDA(p0.create()); FNN_CUDA(p1.create());
         for (int64_t it = 0; it < max_iters; ++it) {
             const bool sample = (it % c->o.profile_every) == 0;
             if (sample) {
@@ -1188,7 +1198,6 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
             launch_rest(c);
             launches += c->launches_per_iter(); ++scans;
         }
-        cudaEventDestroy(p0); cudaEventDestroy(p1);
         FNN_CUDA(cudaGetLastError());
     } else if (c->o.use_graph) {
         constexpr int GI = 16;  // iterations per graph
@@ -1234,10 +1243,12 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     const int n_amalg = c->h_st->n_amalg;
     std::vector<int> lg(5 * (size_t)std::max(n_amalg, 1));
     FNN_CUDA(cudaMemcpy(lg.data(), c->amalg, sizeof(int) * 5 * n_amalg, cudaMemcpyDeviceToHost));
-    expand_order(n, lg, n_amalg, c->h_st->final3, ordering);
+    if (!expand_order(n, lg, n_amalg, c->h_st->final3, ordering)) {
+        fnn::set_error("amalgamation log does not expand to a cycle over %lld taxa", (long long)n);
+        return FNN_E_STATE;
+    }
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     c->stats.order_ms = ms;
     c->stats.iterations = c->h_st->iter;
     c->stats.kernel_launches = launches;
@@ -1334,6 +1345,8 @@ extern "C" int fnn_ctx_connect(fnn_ctx* c, int32_t rank, int32_t world, const vo
     }
     if (!c->have_tmap) { fnn::set_error("fnn_ctx_connect: the sharded scan needs the TMA selection kernel"); return FNN_E_UNSUPPORTED; }
     FNN_CUDA(cudaSetDevice(c->o.device));
+    for (int r = 0; r < MAX_WORLD; ++r)   // a second connect replaces the first wiring
+        if (c->opened[r]) { cudaIpcCloseMemHandle(c->opened[r]); c->opened[r] = nullptr; }
     PeerTable pt;
     memset(&pt, 0, sizeof(pt));
     for (int r = 0; r < world; ++r) {
