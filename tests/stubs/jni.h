@@ -1,0 +1,36 @@
+/* Minimal stand-in for <jni.h>: ONLY for syntax-checking integration/fastnn_jni.c in an image without a JDK
+ * (tests/test_abi.py).  Types and the handful of JNIEnv entries the shim uses, with the JNI specification's signatures. */
+#ifndef FNN_STUB_JNI_H
+#define FNN_STUB_JNI_H
+#include <stdint.h>
+typedef int32_t jint;
+typedef int64_t jlong;
+typedef uint8_t jboolean;
+typedef double jdouble;
+typedef jint jsize;
+typedef void* jobject;
+typedef jobject jclass;
+typedef jobject jstring;
+typedef jobject jarray;
+typedef jarray jobjectArray;
+typedef jarray jintArray;
+typedef jarray jdoubleArray;
+#define JNIEXPORT __attribute__((visibility("default")))
+#define JNICALL
+struct JNINativeInterface_;
+typedef const struct JNINativeInterface_* JNIEnv;
+struct JNINativeInterface_ {
+    jclass (*FindClass)(JNIEnv*, const char*);
+    jint (*ThrowNew)(JNIEnv*, jclass, const char*);
+    void (*DeleteLocalRef)(JNIEnv*, jobject);
+    jobject (*GetObjectArrayElement)(JNIEnv*, jobjectArray, jsize);
+    const char* (*GetStringUTFChars)(JNIEnv*, jstring, jboolean*);
+    void (*ReleaseStringUTFChars)(JNIEnv*, jstring, const char*);
+    jintArray (*NewIntArray)(JNIEnv*, jsize);
+    jdoubleArray (*NewDoubleArray)(JNIEnv*, jsize);
+    void (*GetIntArrayRegion)(JNIEnv*, jintArray, jsize, jsize, jint*);
+    void (*SetIntArrayRegion)(JNIEnv*, jintArray, jsize, jsize, const jint*);
+    void (*GetDoubleArrayRegion)(JNIEnv*, jdoubleArray, jsize, jsize, jdouble*);
+    void (*SetDoubleArrayRegion)(JNIEnv*, jdoubleArray, jsize, jsize, const jdouble*);
+};
+#endif

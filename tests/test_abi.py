@@ -51,3 +51,21 @@ def test_fails_loudly_without_gpu():
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
     with pytest.raises(fnn.FastNNError):
         fnn.Context(10)
+
+
+def test_jni_shim_compiles_and_links_against_the_abi(tmp_path):
+    """integration/fastnn_jni.c (the reference-side binding of INTEGRATION.md) against a stub jni.h: every libfastnn entry
+    point it calls exists with a compatible prototype, and the four natives of integration/NativeNN.java are exported."""
+    import subprocess
+    so = tmp_path / "libfastnn_jni.so"
+    libdir = os.path.dirname(fnn.lib_path())
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "integration", "fastnn_jni.c"), "-L", libdir, "-lfastnn", "-Wl,--no-undefined", "-Wl,--allow-shlib-undefined", "-o", str(so)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(so)], capture_output=True, text=True).stdout
+    with open(os.path.join(ROOT, "integration", "NativeNN.java")) as f:
+        natives = re.findall(r"static native [\w\[\]]+ (\w+)\(", f.read())
+    assert sorted(natives) == ["network", "order", "orderFromFile", "splitWeights"]
+    for name in natives:
+        assert f"Java_nnet_NativeNN_{name}" in syms
