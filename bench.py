@@ -10,17 +10,24 @@ between the GPU and the CPU arms; `ms_per_step` is the ordering's wall time.
 
   value     inputs resident in HBM (device matrix restored from a pristine device copy each step)
   e2e       the same through the reference-facing one-shot C-ABI call fnn_order() with a pinned
-            HOST matrix: cudaMalloc + H2D of n*n*8 bytes + ordering + D2H of the ordering, all timed
-  roofline  the selection kernel k_scan: algorithmic bytes per launch / CUDA-event launch time,
+            HOST matrix: H2D of n*n*8 bytes + ordering + D2H of the ordering, all timed
+  roofline  the selection kernel k_scan_tma: algorithmic bytes per launch / CUDA-event launch time,
             sampled every 16th iteration inside a dedicated profiled run of the same workload
+  parity    BEFORE the timed region, at the SAME world size: orderings (and per-iteration traces) of
+            n=1500 and n=5000 (> the 4096-node sharding threshold) against the CPU oracle, plus the
+            sha256 of the n=20000 ordering (N>1 lines also carry the hash of an un-wired 1-GPU run)
+  configs   one timed run each of the other BASELINE configs that fit the step budget (N=1 only)
   cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/, "port": the JAR
-            cannot run here - no JVM) on a bounded sample (smaller n), all host threads.
+            cannot run here - no JVM) on bounded samples, all host threads and 1 thread, with the
+            c*n^3 fit that extrapolates the CPU wall time to the workload's n.
 
-N>1: one process per GPU, ONE job: the selection scan (the Theta(n^3) part) is sharded across the
-ranks, the per-rank (Q,i,j) partial min-locs are exchanged through peer-mapped mailboxes over NVLink
-inside the kernels, the Theta(n^2) update is replicated -> scaling is "strong".
+N>1: one process per GPU, ONE job (fixed total work -> "strong" scaling at every N): the selection
+scan (the Theta(n^3) part) is sharded across the ranks, the per-rank (Q,i,j) partial min-locs are
+exchanged through peer-mapped mailboxes over NVLink inside the kernels, the Theta(n^2) update is
+replicated.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -33,6 +40,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "neighbornet_canonical_order_algorithmic_hbm_throughput"
 UNIT = "GB/s"
+SCALING = "strong"   # one fixed job at every N
 
 
 def host_threads():
@@ -42,15 +50,26 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_reference_run(n, seed, threads):
-    """One canonical ordering on the CPU restatement; returns (seconds, algorithmic bytes)."""
+def sha(o):
+    return hashlib.sha256(o.tobytes()).hexdigest()[:16]
+
+
+def cpu_reference_run(n, seed, threads, want_order=False):
+    """One canonical ordering on the CPU restatement; returns (seconds, algorithmic bytes[, ordering])."""
     import oracle
     from fastneighbornet_b200 import synth
     D = synth.additive_noise_matrix(n, seed, 0.05)
     t0 = time.perf_counter()
-    _, _, info = oracle.order(D, mode="canonical", want_trace=False, threads=threads)
+    o, _, info = oracle.order(D, mode="canonical", want_trace=False, threads=threads)
     dt = time.perf_counter() - t0
-    return dt, info["alg_bytes"]
+    return (dt, info["alg_bytes"], o) if want_order else (dt, info["alg_bytes"])
+
+
+def cubic_fit(ns, ts):
+    """least-squares c in t = c*n^3"""
+    num = sum(t * n ** 3 for n, t in zip(ns, ts))
+    den = sum(float(n) ** 6 for n in ns)
+    return num / den
 
 
 class ClockSampler:
@@ -113,9 +132,25 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+WORKLOAD = ("canonical Neighbor-Net ordering (-mode Canonical -order), n={n} taxa, synthetic additive tree + 5% noise "
+            "(BASELINE metric 'n=20k'; fits one GPU: {gb:.1f} GB fp64 matrix)")
+
+
+def workload_config(args, world):
+    return {
+        "workload": WORKLOAD.format(n=args.n, gb=args.n * args.n * 8 / 1e9),
+        "n_taxa": args.n, "mode": "canonical", "eps": 0.05,
+        "parallelism": "single GPU" if world == 1 else f"{world} GPUs: scan sharded by tile, P2P min-loc mailbox exchange, replicated update",
+        "l2": f"input matrix {args.n * args.n * 8 / 1e6:.0f} MB >> 126 MB L2; no explicit flush",
+    }
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm (restatement; the JAR needs a JVM that this
-    image does not have) on a bounded sample of the workload, all host threads, rank 0 only."""
+    """--impl reference: the reference's own CPU algorithm (restatement; the JAR needs a JVM that this image does not have).
+    Each step = one canonical ordering of a BOUNDED SAMPLE (n = --ref-n) of the workload with all host threads
+    (NeighborNetCanonical's thread partition, NeighborNetCanonical.java:180-206); rank 0 only.  The line says which n it ran
+    (`config.n_taxa`), adds the `-threads 1` arm, and fits t = c*n^3 on n in --fit-n to extrapolate the CPU wall time to the
+    workload's n (flagged `extrapolated`)."""
     if rank != 0:
         return
     threads = host_threads()
@@ -128,27 +163,40 @@ def run_reference(args, rank, world):
         tot_t += dt
         tot_b += b
     val = tot_b / tot_t / 1e9
-    sample = f"canonical ordering, n={n} (same generator, eps=0.05), {threads} threads, NeighborNetCanonical thread partition"
+    ms = 1e3 * tot_t / args.steps
+    # c*n^3 fits: all threads on --fit-n, 1 thread on --fit-n1
+    fit_ns = [int(x) for x in args.fit_n.split(",") if x]
+    fit_ts = []
+    for fn_ in fit_ns:
+        fit_ts.append(ms / 1e3 if fn_ == n else cpu_reference_run(fn_, 1, threads)[0])
+    c_mt = cubic_fit(fit_ns, fit_ts)
+    fit1_ns = [int(x) for x in args.fit_n1.split(",") if x]
+    fit1 = [cpu_reference_run(fn_, 1, 1) for fn_ in fit1_ns]
+    c_1t = cubic_fit(fit1_ns, [t for t, _ in fit1])
+    n1 = fit1_ns[-1]
+    val1 = fit1[-1][1] / fit1[-1][0] / 1e9
+    sample = (f"canonical ordering of a bounded sample, n={n} of the n={args.n} workload (same generator, eps=0.05), {threads} threads, "
+              f"NeighborNetCanonical thread partition")
+    cfg = workload_config(args, 1)
+    cfg.update({"n_taxa": n, "sample_of_n_taxa": args.n, "parallelism": f"CPU, {threads} threads",
+                "l2": f"host caches; sample matrix {n * n * 8 / 1e6:.0f} MB"})
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, world),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": SCALING,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "value_1thread": val1, "sample_1thread": f"n={n1}, {fit1[-1][0]:.1f} s on 1 thread"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "extrapolated": {
+            "extrapolated": True, "n_taxa": args.n, "model": "t = c*n^3 (least squares)",
+            "threads_all": {"cores": threads, "fit_n": fit_ns, "fit_seconds": fit_ts, "c": c_mt, "seconds_at_workload_n": c_mt * args.n ** 3,
+                            "seconds_at_100k": c_mt * 1e15},
+            "threads_1": {"cores": 1, "fit_n": fit1_ns, "fit_seconds": [t for t, _ in fit1], "c": c_1t,
+                          "seconds_at_workload_n": c_1t * args.n ** 3, "seconds_at_100k": c_1t * 1e15},
+        },
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args, world):
-    return {
-        "workload": f"canonical Neighbor-Net ordering (-mode Canonical -order), n={args.n} taxa, synthetic additive tree + 5% noise "
-                    f"(BASELINE metric 'n=20k'; fits one GPU: {args.n * args.n * 8 / 1e9:.1f} GB fp64 matrix)",
-        "n_taxa": args.n, "mode": "canonical", "eps": 0.05,
-        "parallelism": "single GPU" if world == 1 else f"{world} GPUs: scan sharded by tile, P2P min-loc mailbox exchange, replicated update",
-        "l2": f"input matrix {args.n * args.n * 8 / 1e6:.0f} MB >> 126 MB L2; no explicit flush",
-    }
 
 
 def main():
@@ -159,8 +207,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=20000)
     ap.add_argument("--ref-n", type=int, default=2000, help="taxa of the bounded CPU sample")
+    ap.add_argument("--fit-n", default="2000,5000,10000", help="reference arm: sizes of the all-threads c*n^3 fit")
+    ap.add_argument("--fit-n1", default="1000,1500,2000", help="reference arm: sizes of the 1-thread c*n^3 fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -175,6 +227,7 @@ def main():
     import torch
     import torch.distributed as dist
     import fastneighbornet_b200 as fnn
+    from fastneighbornet_b200 import synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
@@ -189,6 +242,38 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def gather_hashes(h):
+        if world == 1:
+            return [h]
+        hs = [None] * world
+        dist.all_gather_object(hs, h)
+        return hs
+
+    # ---- parity at THIS world size, before anything is timed (VERDICT r1 "next" 1a)
+    parity = None
+    if not args.no_parity:
+        import oracle
+        parity = {"world": world, "ok": True, "cases": []}
+        for pn, pseed in ((1500, 7), (5000, 3)):
+            D = synth.additive_noise_matrix(pn, pseed, 0.05)
+            with fnn.Context(pn, device=local_rank, record_trace=1) as pc:
+                if world > 1:
+                    pc.connect_torch()
+                pc.load_host(D)
+                po = pc.order()
+                ptr = pc.trace()
+            hs = gather_hashes(sha(po))
+            case = {"n": pn, "ordering_sha256": hs[0], "ranks_agree": len(set(hs)) == 1}
+            if rank == 0:
+                o_ref, tr_ref, _ = oracle.order(D, threads=host_threads())
+                case["ordering_equals_oracle"] = bool((po == o_ref).all())
+                case["trace_equals_oracle"] = bool(ptr.shape == tr_ref.shape and (ptr == tr_ref).all())
+                case["oracle_sha256"] = sha(o_ref)
+                parity["ok"] = parity["ok"] and case["ordering_equals_oracle"] and case["trace_equals_oracle"] and case["ranks_agree"]
+            parity["cases"].append(case)
+            del D
+        barrier()
 
     n = args.n
     seed = 1   # every rank holds the same matrix (one job)
@@ -209,6 +294,15 @@ def main():
     pristine.copy_(view)
     torch.cuda.synchronize()
 
+    # N>1: the hash an un-wired single-GPU run of the same workload gives (rank 0), for the driver to compare across N
+    sha_n1 = None
+    if world > 1 and not args.no_parity:
+        if rank == 0:
+            with fnn.Context(n, device=local_rank, use_graph=1) as c1:
+                c1.load_device(pristine.data_ptr(), ld)
+                sha_n1 = sha(c1.order())
+        barrier()
+
     def step():
         ctx.load_device(pristine.data_ptr(), ld)
         return ctx.order()
@@ -220,6 +314,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t0 = time.perf_counter()
     dev_ms, launches, alg_bytes = 0.0, 0, 0.0
+    o = ordering0
     for _ in range(args.steps):
         o = step()
         st = ctx.stats()
@@ -229,8 +324,10 @@ def main():
     barrier()
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
-    assert (o == ordering0).all(), "ordering changed between identical steps"
-    # max over ranks of the elapsed time; bytes summed over ranks
+    if ordering0 is not None:
+        assert (o == ordering0).all(), "ordering changed between identical steps"
+    picks = (st["picks_certified"], st["picks_exact"])
+    # max over ranks of the elapsed time; launches summed over ranks
     if world > 1:
         t = torch.tensor([elapsed, dev_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -239,6 +336,13 @@ def main():
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
         launches = int(b[0])   # alg_bytes is the ONE job's (identical on every rank)
     value = alg_bytes / elapsed / 1e9
+    hashes = gather_hashes(sha(o))
+    if parity is not None:
+        parity["workload_ranks_agree"] = len(set(hashes)) == 1
+        parity["ok"] = parity["ok"] and parity["workload_ranks_agree"]
+        if sha_n1 is not None:
+            parity["workload_equals_single_gpu"] = (hashes[0] == sha_n1)
+            parity["ok"] = parity["ok"] and parity["workload_equals_single_gpu"]
 
     # ---- e2e: one-shot C-ABI call with a pinned HOST matrix
     e2e = None
@@ -263,7 +367,7 @@ def main():
             oe = e2e_step()
         barrier()
         e2e_elapsed = time.perf_counter() - t0
-        assert (oe == ordering0).all(), "e2e ordering differs from the device-resident run"
+        assert (oe == o).all(), "e2e ordering differs from the device-resident run"
         if world > 1:
             t = torch.tensor([e2e_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -271,23 +375,25 @@ def main():
         e2e = {"value": alg_bytes / e2e_elapsed / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * n * 8 * world,
                "d2h_bytes_per_step": (n + 1) * 4 * world, "ms_per_step": 1e3 * e2e_elapsed / args.steps}
         if world == 1:
-            ctx = fnn.Context(n, device=local_rank, use_graph=1)
+            fnn.release_cache()
+        del host, Dh
 
-    # ---- roofline of the dominant kernel (k_scan), rank 0 only
-    roofline, cpu_baseline = None, None
+    # ---- roofline of the dominant kernel (k_scan_tma), rank 0 only
+    roofline, cpu_baseline, configs = None, None, None
+    peak, peak_src = measured_peak()
     if rank == 0:
         pctx = fnn.Context(n, device=local_rank, profile_every=16)
         pctx.load_device(pristine.data_ptr(), ld)
         pctx.order()
         ps = pctx.stats()
         pctx.close()
-        peak, peak_src = measured_peak()
         achieved = ps["prof_scan_bytes"] / (ps["prof_scan_ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_scan_tma", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                     "traffic": None, "peak_source": peak_src, "samples": ps["prof_scan_samples"],
                     "avg_launch_ms": ps["prof_scan_ms"] / max(1, ps["prof_scan_samples"]),
                     "alg_bytes_per_launch": ps["prof_scan_bytes"] / max(1, ps["prof_scan_samples"]),
-                    "scan_share_of_step": ((ps["prof_scan_ms"] * 16) / (1e3 * elapsed / args.steps)) if world == 1 else None}
+                    "scan_share_of_step": ((ps["prof_scan_ms"] * 16) / (1e3 * elapsed / args.steps)) if world == 1 else None,
+                    "whole_job_frac": value / (peak * world)}
         if world > 1:
             roofline["note"] = "kernel profiled on rank 0 as a single-GPU run of the same workload (each rank launches it on 1/world of the tiles)"
         tfile = os.path.join(ROOT, "profiles", "scan_traffic.json")
@@ -297,15 +403,49 @@ def main():
                     roofline["traffic"] = json.load(f).get("traffic_bytes_per_launch")
             except Exception:
                 pass
-        if not args.no_cpu_baseline and world == 1:   # reported at N=1 only
-            threads = host_threads()
-            dt, b = cpu_reference_run(args.ref_n, 1, threads)
-            cpu_baseline = {"value": b / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": f"one canonical ordering at n={args.ref_n} (same generator), {dt:.1f} s on {threads} threads"}
-            n1 = min(args.ref_n, 1500)   # the reference's -threads 1 figure on a smaller sample
-            dt1, b1 = cpu_reference_run(n1, 1, 1)
-            cpu_baseline["value_1thread"] = b1 / dt1 / 1e9
-            cpu_baseline["sample_1thread"] = f"n={n1}, {dt1:.1f} s on 1 thread"
+    del pristine
+    if world == 1:
+        try:
+            ctx.close()
+        except Exception:
+            pass
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs that fit the step budget, one timed run each (N=1 only)
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = []
+
+        def timed(label, cn, cseed, eps, unit_bytes_key, **opts):
+            with fnn.Context(cn, device=local_rank, **opts) as c:
+                c.synth(cseed, eps)
+                c.order()           # warm-up (graph instantiation, clocks)
+                c.synth(cseed, eps)
+                torch.cuda.synchronize()
+                t0_ = time.perf_counter()
+                oo = c.order()
+                dt = time.perf_counter() - t0_
+                s_ = c.stats()
+            b_ = s_[unit_bytes_key] + (s_["scan_alg_bytes"] if unit_bytes_key != "scan_alg_bytes" else 0.0)
+            return {"config": label, "n_taxa": cn, "ms": 1e3 * dt, "alg_bytes": b_, "achieved": b_ / dt / 1e9, "unit": "GB/s",
+                    "frac": b_ / dt / 1e9 / peak, "iterations": s_["iterations"], "gpu_launches": s_["kernel_launches"],
+                    "strategy_units": s_["strategy_units"], "ordering_sha256": sha(oo)}
+
+        configs.append(timed("configs[0]: Canonical -order, 200-taxon additive tree (eps=0)", 200, 1, 0.0, "scan_alg_bytes"))
+        configs.append(timed("configs[2] without -additive: Relaxed, 20000 taxa (row scans: SURVEY 8d K7 bytes + the canonical tail's scan bytes)",
+                             20000, 3, 0.05, "strategy_alg_bytes", mode="relaxed", seed=7))
+        configs.append(timed("configs[3] at the size that fits the step budget: Random_NLOGN -mult 5, 10000 taxa (samples: SURVEY 8d K9 bytes + tail scan bytes)",
+                             10000, 4, 0.05, "strategy_alg_bytes", mode="random_nlogn", mult=5, seed=7))
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:   # reported at N=1 only
+        threads = host_threads()
+        dt, b = cpu_reference_run(args.ref_n, 1, threads)
+        cpu_baseline = {"value": b / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"one canonical ordering at n={args.ref_n} (bounded sample of the n={n} workload, same generator), "
+                                  f"{dt:.1f} s on {threads} threads"}
+        n1 = min(args.ref_n, 1500)   # the reference's -threads 1 figure on a smaller sample
+        dt1, b1 = cpu_reference_run(n1, 1, 1)
+        cpu_baseline["value_1thread"] = b1 / dt1 / 1e9
+        cpu_baseline["sample_1thread"] = f"n={n1}, {dt1:.1f} s on 1 thread"
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -313,10 +453,12 @@ def main():
         return
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "device_ms_per_step": dev_ms / args.steps, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "ordering_sha256": hashes[0], "ordering_sha256_single_gpu": sha_n1 if world > 1 else hashes[0], "parity": parity,
+        "picks": {"certified": picks[0], "exact_sums": picks[1]},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "configs": configs,
     }
     print(json.dumps(line), flush=True)
 

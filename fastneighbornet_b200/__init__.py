@@ -26,5 +26,6 @@ from .api import (  # noqa: F401
     read_phylip,
     write_nexus,
     java_double_str,
+    release_cache,
 )
 from . import synth  # noqa: F401

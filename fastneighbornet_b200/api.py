@@ -60,7 +60,7 @@ ABI_SYMBOLS = [
     "fnn_ctx_load_host", "fnn_ctx_load_device", "fnn_ctx_synth", "fnn_ctx_read_matrix", "fnn_ctx_order",
     "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums", "fnn_seq_sum",
     "fnn_split_weights", "fnn_csw_matvec", "fnn_ctx_ipc_handle", "fnn_ctx_connect", "fnn_weighted_splits", "fnn_network",
-    "fnn_phylip_taxa", "fnn_read_phylip", "fnn_write_nexus", "fnn_java_double_to_string",
+    "fnn_phylip_taxa", "fnn_read_phylip", "fnn_write_nexus", "fnn_java_double_to_string", "fnn_release_cache",
 ]
 
 
@@ -96,6 +96,8 @@ def lib():
         L.fnn_ctx_ipc_handle.argtypes = [vp, ctypes.c_char_p]
         L.fnn_ctx_connect.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p]
         L.fnn_order.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
+        L.fnn_release_cache.argtypes = []
+        L.fnn_release_cache.restype = None
         L.fnn_rowsums.argtypes = [ctypes.POINTER(fnn_opts), c_dp, ctypes.c_int64, c_dp]
         L.fnn_split_weights.argtypes = [ctypes.POINTER(fnn_opts), ctypes.POINTER(ctypes.c_int32), c_dp, ctypes.c_int64, c_dp,
                                         ctypes.POINTER(ctypes.c_int64)]
@@ -126,12 +128,24 @@ def device_count():
     return lib().fnn_device_count()
 
 
+# A/B switches carried in fnn_opts.reserved (include/fastnn.h): name -> (index, bit or None for "whole int")
+_RESERVED = {"serial_chain": (1, None), "no_overlap": (5, 1), "force_exact_pick": (5, 2), "csw_graph_path": (4, None),
+             "csw_literal_order": (4, None)}
+
+
 def default_opts(**kw):
     o = fnn_opts()
     lib().fnn_default_opts(ctypes.byref(o))
     for k, v in kw.items():
         if k == "mode" and isinstance(v, str):
             v = MODES[v.lower()]
+        if k in _RESERVED:
+            idx, bit = _RESERVED[k]
+            if bit is None:
+                o.reserved[idx] = int(v)
+            elif v:
+                o.reserved[idx] |= bit
+            continue
         setattr(o, k, int(v))
     return o
 
@@ -229,7 +243,12 @@ class Context:
     def stats(self):
         s = fnn_stats()
         _check(lib().fnn_ctx_stats(self._h, ctypes.byref(s)))
-        return {f: getattr(s, f) for f, _ in fnn_stats._fields_ if f != "reserved"}
+        out = {f: getattr(s, f) for f, _ in fnn_stats._fields_ if f != "reserved"}
+        out["picks_certified"] = int(s.reserved[0])   # 4-candidate picks decided by the bounded parallel ComputeRx sums
+        out["picks_exact"] = int(s.reserved[1])       # ... that needed the exact left-to-right sums
+        out["strategy_alg_bytes"] = float(s.reserved[2])   # Relaxed row scans / Random samples
+        out["strategy_units"] = int(s.reserved[3])
+        return out
 
 
 def order(D=None, phylip_path=None, n=None, **opts):
@@ -243,6 +262,11 @@ def order(D=None, phylip_path=None, n=None, **opts):
                            phylip_path.encode() if phylip_path else None, int(n),
                            out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
     return out
+
+
+def release_cache():
+    """Free the context the one-shot seam keeps between calls (fnn_release_cache)."""
+    lib().fnn_release_cache()
 
 
 def rowsums(D, **opts):

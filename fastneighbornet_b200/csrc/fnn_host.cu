@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include "fastnn.h"
 #include "fnn_common.h"
 
@@ -22,6 +23,21 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 }  // namespace fnn
+
+// The one-shot seam keeps its last context (device matrix, node tables, tensor map, instantiated CUDA graph) so that a
+// host which orders several matrices of one size - the reference CLI in a loop, a bootstrap - pays cudaMalloc, the
+// tensor-map encode and the graph instantiation once.  fnn_release_cache() gives the memory back.
+namespace {
+std::mutex g_cache_mu;
+fnn_ctx* g_cache = nullptr;
+fnn_opts g_cache_opts;
+int64_t g_cache_n = 0;
+}  // namespace
+
+extern "C" void fnn_release_cache(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache) { fnn_ctx_destroy(g_cache); g_cache = nullptr; }
+}
 
 extern "C" int fnn_order(const fnn_opts* o, const double* Dh, const char* phylip_path, int64_t n, int32_t* ordering) {
     if (!ordering || n < 1 || ((Dh == nullptr) == (phylip_path == nullptr))) {
@@ -39,12 +55,19 @@ extern "C" int fnn_order(const fnn_opts* o, const double* Dh, const char* phylip
         if (rc) return rc;
         Dh = file_D.data();
     }
-    fnn_ctx* c = nullptr;
-    int rc = fnn_ctx_create(o, n, &c);
-    if (rc) return rc;
-    rc = fnn_ctx_load_host(c, Dh);
-    if (!rc) rc = fnn_ctx_order(c, ordering);
-    fnn_ctx_destroy(c);
+    fnn_opts key;
+    if (o) key = *o; else fnn_default_opts(&key);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache && (g_cache_n != n || memcmp(&g_cache_opts, &key, sizeof(key)) != 0)) { fnn_ctx_destroy(g_cache); g_cache = nullptr; }
+    if (!g_cache) {
+        int rc = fnn_ctx_create(&key, n, &g_cache);
+        if (rc) { g_cache = nullptr; return rc; }
+        g_cache_opts = key;
+        g_cache_n = n;
+    }
+    int rc = fnn_ctx_load_host(g_cache, Dh);
+    if (!rc) rc = fnn_ctx_order(g_cache, ordering);
+    if (rc) { fnn_ctx_destroy(g_cache); g_cache = nullptr; }   // do not reuse a context whose run failed
     return rc;
 }
 

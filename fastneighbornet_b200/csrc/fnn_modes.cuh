@@ -255,9 +255,11 @@ k_random_eval(const double* __restrict__ D, int64_t ld, const double* __restrict
     const long long total = ws->count;
     double bq = INFINITY;
     unsigned long long bk = ~0ull;
+    unsigned long long abytes = 0;   // 8*(1|2|4) + 16 bytes per sample
     for (long long k = (long long)blockIdx.x * blockDim.x + tid; k < total; k += (long long)gridDim.x * blockDim.x) {
         const int2 pr = pairs[k];
         const int sp = p2s[pr.x], sq = p2s[pr.y];
+        abytes += 8ull * (unsigned)((1 + (sp < P2)) * (1 + (sq < P2))) + 16ull;
         const double q = (cm2 * dpq_roles(D, ld, sp, sq, P2) - Sx[sp]) - Sx[sq];
         if (bk == ~0ull || q < bq || (q == bq && (unsigned long long)k < bk)) { bq = q; bk = (unsigned long long)k; }
     }
@@ -269,7 +271,8 @@ k_random_eval(const double* __restrict__ D, int64_t ld, const double* __restrict
         const unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, off);
         take(oq, ok);
     }
-    if ((tid & 31) == 0) { wq[tid >> 5] = bq; wk[tid >> 5] = bk; }
+    for (int off = 16; off > 0; off >>= 1) abytes += __shfl_down_sync(0xffffffffu, abytes, off);
+    if ((tid & 31) == 0) { wq[tid >> 5] = bq; wk[tid >> 5] = bk; if (abytes) atomicAdd(&st->strat_bytes, abytes); }
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < 8; ++w) take(wq[w], wk[w]);
@@ -285,6 +288,7 @@ k_random_eval(const double* __restrict__ D, int64_t ld, const double* __restrict
         const int2 pr = pairs[bk];
         st->cx_pos = pr.x;   // Cx = p, Cy = q (:173-176)
         st->cy_pos = pr.y;
+        st->strat_units += (unsigned long long)total;
         *ticket = 0;
     }
 }
@@ -474,6 +478,9 @@ k_relaxed_select(const double* __restrict__ D, int64_t ld, const double* __restr
         if (r == relaxed::REQ_SCAN) {
             const int cnt = block_rowmin(D, ld, Sx, pos, p2s, m, P2, cm2, M.req_pos, M.tiepool + M.tie_used, relaxed::tie_room(M));
             if (tid == 0) {
+                // a row scan reads the row (two rows if p is paired) and Sx
+                st->strat_bytes += 8ull * (unsigned long long)m * (unsigned)(1 + (p2s[M.req_pos] < P2)) + 8ull * (unsigned long long)m;
+                st->strat_units += 1;
                 if (cnt < 0) M.error = 3;
                 else relaxed::commit_scan(M, cnt);
             }

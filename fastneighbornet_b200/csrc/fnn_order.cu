@@ -7,9 +7,11 @@
 // then the circular-order expansion (:246-325).
 //
 // How this file does it (B200-first, not a translation):
-//   * The whole agglomeration state lives in HBM and the loop runs device-side: five kernels
-//     per iteration, no host round trip, replayed as a CUDA graph.  The host only expands
-//     the amalgamation log at the end (expandNodes stays on the host).
+//   * The whole agglomeration state lives in HBM and the loop runs device-side: five kernels on the
+//     critical path of an iteration (scan, k_rx_stage, k_pick, k_rows, k_scatter) plus one on a forked
+//     graph branch (k_chain_patch, overlapped with the NEXT iteration's scan), no host round trip,
+//     replayed as a CUDA graph.  The host only expands the amalgamation log at the end (expandNodes
+//     stays on the host).
 //   * Physical layout != reference layout.  The live nodes occupy matrix slots [0,m):
 //     slots [0,P2) hold the paired clusters as aligned (rep, non-rep) slot pairs, slots
 //     [P2,m) hold the singletons.  Every cluster pair's 1/2/4 cross entries are then one or
@@ -20,9 +22,14 @@
 //   * The reference's scan order is carried as data: pos[slot] is the node's index in the
 //     Java netNodes[] array; the fused min-loc reduces on the key (Q, i, j) = (value, higher
 //     position, lower position), which is exactly "first strict minimum in (i, j<i) order".
-//   * Bit-exactness: compiled with --fmad=false; sums that the reference accumulates
-//     sequentially (ComputeRx, u.Sx) are summed sequentially in position order by one lane
-//     reading shared-memory tiles staged by the rest of the block.
+//   * Bit-exactness: compiled with --fmad=false.  u.Sx (a persistent left-to-right sum, :530-535) is
+//     reproduced bit for bit by the verified binade-collapsed summation of fnn_exact_sum.cuh, OFF the
+//     critical path: the next scan runs with the new cluster masked (Sx = -inf) while k_chain_patch
+//     finishes u.Sx and evaluates the new cluster's 2 rows exactly; the two partial min-locs are merged by
+//     whichever finishes last.  The <=4 ComputeRx sums (:549-561) only feed the 4-candidate pick, so a
+//     parallel sum with a rigorous rounding bound decides it whenever the candidates are separated by
+//     more than the bound (certified pick); otherwise, and always when a trace is recorded, the exact
+//     left-to-right sums decide.
 //
 // No CPU fallback: every entry point fails with FNN_E_NODEVICE when there is no GPU.
 #include <cuda_runtime.h>
@@ -75,7 +82,28 @@ struct DevState {
     unsigned long long rng;       // java.util.Random state (48 bits)
     double Dmax;                  // max |D| at load time (slack of the scan's filter, fnn_scan_tma.cuh)
     double alg_bytes;             // running sum of the selection scan's algorithmic bytes
+    // ---- chain off the critical path: the cluster created by the previous iteration is masked in the scan
+    int mask_su;                  // base slot of the cluster whose u.Sx is still being summed (-1: none)
+    unsigned int join_ticket;     // scan's last block and k_chain_patch: the second to arrive merges and selects
+    unsigned int commit_ticket;   // k_scatter: the last block to finish commits (m, c, P2, iter, done)
+    int pad1;
+    double scanQ, patchQ;         // partial min-locs: the masked scan / the new cluster's rows
+    unsigned long long scanKey, patchKey;
+    // ---- certified pick
+    long long cert_ok, cert_fail; // picks decided by the bounded parallel sums / by the exact chains
+    // ---- algorithmic bytes of the Relaxed row scans (K7) / Random samples (K9), SURVEY §8(d)
+    unsigned long long strat_bytes;
+    unsigned long long strat_units;   // row scans / samples
+    // ---- optional in-graph timeline (env FNN_TIMELINE=iter0,count,file): globaltimer stamps of the kernels of a window of
+    // iterations, the only way to see the real overlap and gaps inside a graph replay
+    unsigned long long* tl;
+    int tl_iter0, tl_count;
 };
+constexpr int TL_EVENTS = 16;
+enum { TL_SCAN0 = 0, TL_SCAN1, TL_RX0, TL_RX1, TL_PICK0, TL_PICK1, TL_ROWS0, TL_ROWS1, TL_SCAT0, TL_SCAT1, TL_CHAIN0, TL_CHAIN1,
+       TL_PATCH1, TL_SEL0, TL_SEL1 };
+
+constexpr int RX_BLOCKS_MAX = 1024;   // per-block partial ComputeRx sums: [block][8] = 4 sums + 4 sums of |terms|
 
 struct Partial { double q; unsigned long long key; };
 
@@ -87,14 +115,37 @@ constexpr int MAX_WORLD = 8;
 // below this many active nodes a full scan costs less than the cross-GPU exchange: every rank scans everything itself
 constexpr int SHARD_MIN_ACTIVE = 4096;
 __device__ __forceinline__ int effective_world(int world, int m) { return m > SHARD_MIN_ACTIVE ? world : 1; }
-// two 16-byte halves, each written with ONE vector store and carrying the tag, so no fence is needed between the
-// payload and the tag: a half is either entirely old or entirely new
-struct __align__(16) MailSlot { double q; long long tag0; unsigned long long key; long long tag1; };
-__device__ __forceinline__ void mail_store(void* p, unsigned long long a, long long b) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+// payload first, then a system-scope fence, then the tag (release); the reader spins on the tag (acquire) and only then
+// reads the payload - no reliance on a 16-byte store being single-copy atomic across NVLink
+struct __align__(32) MailSlot { double q; unsigned long long key; long long tag; long long pad; };
+__device__ __forceinline__ void mail_store_payload(MailSlot* ms, double q, unsigned long long key) {
+    asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(&ms->q), "d"(q) : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(&ms->key), "l"(key) : "memory");
 }
-__device__ __forceinline__ void mail_load(const void* p, unsigned long long& a, long long& b) {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+__device__ __forceinline__ void mail_store_tag(MailSlot* ms, long long tag) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(&ms->tag), "l"(tag) : "memory");
+}
+__device__ __forceinline__ long long mail_load_tag(const MailSlot* ms) {
+    long long t;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(t) : "l"(&ms->tag) : "memory");
+    return t;
+}
+__device__ __forceinline__ void mail_load_payload(const MailSlot* ms, double& q, unsigned long long& key) {
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(q) : "l"(&ms->q) : "memory");
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(key) : "l"(&ms->key) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long MAIL_TIMEOUT_NS = 30ull * 1000000000ull;   // a peer that never posts: give up, do not hang
+__device__ __forceinline__ void tl_stamp(DevState* st, int ev) {
+    unsigned long long* tl = st->tl;
+    if (tl) {
+        const int k = st->iter - st->tl_iter0;
+        if (k >= 0 && k < st->tl_count) tl[k * TL_EVENTS + ev] = global_ns();
+    }
 }
 struct Mailbox { MailSlot slot[2][MAX_WORLD]; };
 struct PeerTable { Mailbox* box[MAX_WORLD]; };
@@ -115,7 +166,7 @@ __device__ void select_body(const int* __restrict__ id, const int* __restrict__ 
 
 // ------------------------------------------------------------------ init kernels
 __global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st, int mode, int mult, int fallback, long long seed,
-                             int rank, int world, long long run_tag) {
+                             int rank, int world, long long run_tag, unsigned long long* tl, int tl_iter0, int tl_count) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) { id[t] = t + 1; pos[t] = t; p2s[t] = t; }
     if (t == 0) {
@@ -124,6 +175,11 @@ __global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st, i
         st->mode = mode; st->mult = mult; st->fallback = fallback;
         st->rank = rank; st->world = world; st->run_tag = run_tag;
         st->rng = ((unsigned long long)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);   // java.util.Random(seed)
+        st->mask_su = -1;
+        st->join_ticket = 1;   // no k_chain_patch precedes the first scan: its arrival is pre-paid
+        st->patchQ = INFINITY; st->patchKey = ~0ull;
+        st->scanQ = INFINITY; st->scanKey = ~0ull;
+        st->tl = tl; st->tl_iter0 = tl_iter0; st->tl_count = tl_count;
     }
 }
 
@@ -147,214 +203,6 @@ __global__ void k_rowsum(const double* __restrict__ D, int64_t ld, int n, double
 __global__ void k_zero_diag(double* D, int64_t ld, int n) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) D[(int64_t)k * ld + k] = 0.0;
-}
-
-// ------------------------------------------------------------------ K2: selection scan
-// Dense lower-triangle stream with fused Q evaluation and (Q, i, j) min-loc.
-// Tile = TR physical rows x 512 columns; thread owns a 16-byte column pair.
-constexpr int SCAN_THREADS = 256;
-constexpr int TILE_W = 2 * SCAN_THREADS;
-
-__device__ __forceinline__ double2 ldg2(const double* p) {
-    return __ldg(reinterpret_cast<const double2*>(p));
-}
-
-template <int TR>
-__global__ void __launch_bounds__(SCAN_THREADS, 2)
-k_scan(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ pos,
-       DevState* st, Partial* partials) {
-    if (st->done || (st->mode != 0 && st->m > st->fallback)) return;   // NetMakerOriginal.java:361-366
-    const int m = st->m, P2 = st->P2;
-    const double cm2 = (double)st->c - 2.0;
-    constexpr int KPB = TILE_W / TR;  // row tiles per 512-row band
-    __shared__ double rSx[TR];
-    __shared__ int rPos[TR];
-    __shared__ Partial wbest[SCAN_THREADS / 32];
-    __shared__ bool amLast;
-
-    double bq = INFINITY;
-    unsigned long long bk = ~0ull;
-
-    const int nRowTiles = (m + TR - 1) / TR;
-    const int gFull = nRowTiles / KPB, rRem = nRowTiles % KPB;
-    const long long total = (long long)KPB * gFull * (gFull + 1) / 2 + (long long)rRem * (gFull + 1);
-
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        // decode t -> (band g, row tile r within band, column tile ct <= g)
-        long long g = (long long)((sqrt(8.0 * (double)t / KPB + 1.0) - 1.0) * 0.5);
-        while ((long long)KPB * g * (g + 1) / 2 > t) --g;
-        while ((long long)KPB * (g + 1) * (g + 2) / 2 <= t) ++g;
-        long long rem = t - (long long)KPB * g * (g + 1) / 2;
-        const int rloc = (int)(rem / (g + 1));
-        const int ct = (int)(rem % (g + 1));
-        const int r0 = ((int)g * KPB + rloc) * TR;
-        const int c0 = ct * TILE_W + 2 * threadIdx.x;
-
-        __syncthreads();
-        if (threadIdx.x < TR && r0 + threadIdx.x < m) {
-            rSx[threadIdx.x] = Sx[r0 + threadIdx.x];
-            rPos[threadIdx.x] = pos[r0 + threadIdx.x];
-        }
-        __syncthreads();
-
-        const int rEnd = min(r0 + TR, m);
-        if (c0 >= m || c0 >= rEnd) continue;
-        const bool colPair = c0 < P2;
-        const bool cv1 = (c0 + 1 < m);
-        const double cS0 = Sx[c0];
-        const int cP0 = pos[c0];
-        const double cS1 = cv1 ? Sx[c0 + 1] : 0.0;
-        const int cP1 = cv1 ? pos[c0 + 1] : 0;
-        const double* base = D + c0;
-
-        if (colPair) {
-            // ---- pair rows x pair column: 2x2 block, role-ordered 4-term mean
-            const int rPairEnd = min(rEnd, P2);
-            int r = r0;
-            constexpr int U = 4;
-            for (; r < rPairEnd; r += 2 * U) {
-                double2 e0[U], e1[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int rr = r + 2 * u;
-                    if (rr < rPairEnd && c0 < rr) {
-                        e0[u] = ldg2(base + (int64_t)rr * ld);
-                        e1[u] = ldg2(base + (int64_t)(rr + 1) * ld);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int rr = r + 2 * u;
-                    if (rr < rPairEnd && c0 < rr) {
-                        const int rp = rPos[rr - r0];
-                        const double rS = rSx[rr - r0];
-                        const bool rowP = rp > cP0;  // the row cluster plays "p" (higher position)
-                        const double t1 = rowP ? e0[u].y : e1[u].x;
-                        const double t2 = rowP ? e1[u].x : e0[u].y;
-                        const double dpq = (((e0[u].x + t1) + t2) + e1[u].y) * 0.25;
-                        const double s1 = rowP ? rS : cS0;
-                        const double s2 = rowP ? cS0 : rS;
-                        const double q = (cm2 * dpq - s1) - s2;
-                        if (q <= bq) {
-                            const unsigned long long key = rowP ? (((unsigned long long)rp << 32) | (unsigned)cP0)
-                                                                : (((unsigned long long)cP0 << 32) | (unsigned)rp);
-                            if (better(q, key, bq, bk)) { bq = q; bk = key; }
-                        }
-                    }
-                }
-            }
-            // ---- single rows x pair column: 2-term mean
-            constexpr int U2 = 8;
-            for (r = max(r0, P2); r < rEnd; r += U2) {
-                double2 e[U2];
-#pragma unroll
-                for (int u = 0; u < U2; ++u)
-                    if (r + u < rEnd) e[u] = ldg2(base + (int64_t)(r + u) * ld);
-#pragma unroll
-                for (int u = 0; u < U2; ++u) {
-                    const int rr = r + u;
-                    if (rr < rEnd) {
-                        const int rp = rPos[rr - r0];
-                        const double rS = rSx[rr - r0];
-                        const bool rowP = rp > cP0;
-                        const double dpq = (e[u].x + e[u].y) * 0.5;
-                        const double s1 = rowP ? rS : cS0;
-                        const double s2 = rowP ? cS0 : rS;
-                        const double q = (cm2 * dpq - s1) - s2;
-                        if (q <= bq) {
-                            const unsigned long long key = rowP ? (((unsigned long long)rp << 32) | (unsigned)cP0)
-                                                                : (((unsigned long long)cP0 << 32) | (unsigned)rp);
-                            if (better(q, key, bq, bk)) { bq = q; bk = key; }
-                        }
-                    }
-                }
-            }
-        } else {
-            // ---- single rows x two single columns
-            constexpr int U2 = 8;
-            for (int r = max(max(r0, P2), c0 + 1); r < rEnd; r += U2) {
-                double2 e[U2];
-#pragma unroll
-                for (int u = 0; u < U2; ++u)
-                    if (r + u < rEnd) e[u] = ldg2(base + (int64_t)(r + u) * ld);
-#pragma unroll
-                for (int u = 0; u < U2; ++u) {
-                    const int rr = r + u;
-                    if (rr < rEnd) {
-                        const int rp = rPos[rr - r0];
-                        const double rS = rSx[rr - r0];
-                        {   // column c0 (c0 < rr holds by loop start)
-                            const bool rowP = rp > cP0;
-                            const double s1 = rowP ? rS : cS0;
-                            const double s2 = rowP ? cS0 : rS;
-                            const double q = (cm2 * e[u].x - s1) - s2;
-                            if (q <= bq) {
-                                const unsigned long long key = rowP ? (((unsigned long long)rp << 32) | (unsigned)cP0)
-                                                                    : (((unsigned long long)cP0 << 32) | (unsigned)rp);
-                                if (better(q, key, bq, bk)) { bq = q; bk = key; }
-                            }
-                        }
-                        if (c0 + 1 < rr) {
-                            const bool rowP = rp > cP1;
-                            const double s1 = rowP ? rS : cS1;
-                            const double s2 = rowP ? cS1 : rS;
-                            const double q = (cm2 * e[u].y - s1) - s2;
-                            if (q <= bq) {
-                                const unsigned long long key = rowP ? (((unsigned long long)rp << 32) | (unsigned)cP1)
-                                                                    : (((unsigned long long)cP1 << 32) | (unsigned)rp);
-                                if (better(q, key, bq, bk)) { bq = q; bk = key; }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-
-    // ---- block min-loc, then the last block to finish reduces the per-block partials
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        double oq = __shfl_down_sync(0xffffffffu, bq, off);
-        unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, off);
-        if (better(oq, ok, bq, bk)) { bq = oq; bk = ok; }
-    }
-    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = Partial{bq, bk};
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < SCAN_THREADS / 32; ++w)
-            if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
-        partials[blockIdx.x] = Partial{bq, bk};
-        __threadfence();
-        unsigned int tk = atomicAdd(&st->ticket, 1u);
-        amLast = (tk == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (amLast) {
-        __threadfence();
-        bq = INFINITY; bk = ~0ull;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += SCAN_THREADS) {
-            const double pq = __ldcg(&partials[b].q);
-            const unsigned long long pk = __ldcg(&partials[b].key);
-            if (better(pq, pk, bq, bk)) { bq = pq; bk = pk; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            double oq = __shfl_down_sync(0xffffffffu, bq, off);
-            unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, off);
-            if (better(oq, ok, bq, bk)) { bq = oq; bk = ok; }
-        }
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = Partial{bq, bk};
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < SCAN_THREADS / 32; ++w)
-                if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
-            st->selQ = bq;
-            st->sel_i = (int)(bk >> 32);
-            st->sel_j = (int)(bk & 0xffffffffu);
-            st->ticket = 0;
-        }
-    }
 }
 
 // ------------------------------------------------------------------ sequential chains
@@ -429,19 +277,31 @@ __device__ void select_body(const int* __restrict__ id, const int* __restrict__ 
     const int m = st->m, P2 = st->P2;
     if (m == 4 && st->c == 2) { st->need_rx = 0; return; }   // special case is handled by k_pick
     const bool strategy = (st->mode != 0 && m > st->fallback);
-    if (effective_world(st->world, m) > 1 && !strategy) {
-        const int par = st->iter & 1;
-        double bq = INFINITY;
-        unsigned long long bk = ~0ull;
-        for (int r = 0; r < st->world; ++r) {
-            const MailSlot* ms = &mail->slot[par][r];
-            const long long want = st->run_tag + (long long)st->iter + 1;   // posted by rank r's k_scan of this iteration
-            unsigned long long qb, k;
-            long long t0, t1;
-            do { mail_load(&ms->q, qb, t0); mail_load(&ms->key, k, t1); } while (t0 != want || t1 != want);
-            const double q = __longlong_as_double((long long)qb);
-            if (better(q, k, bq, bk)) { bq = q; bk = k; }
+    tl_stamp(st, TL_SEL0);
+    if (!strategy) {
+        double bq = st->scanQ;
+        unsigned long long bk = st->scanKey;
+        if (effective_world(st->world, m) > 1) {
+            const int par = st->iter & 1;
+            bq = INFINITY; bk = ~0ull;
+            const long long want = st->run_tag + (long long)st->iter + 1;   // posted by every rank's k_scan of this iteration
+            const unsigned long long t_start = global_ns();
+            for (int r = 0; r < st->world; ++r) {
+                const MailSlot* ms = &mail->slot[par][r];
+                unsigned spins = 0;
+                while (mail_load_tag(ms) != want) {
+                    if ((++spins & 0x3ff) == 0 && global_ns() - t_start > MAIL_TIMEOUT_NS) {
+                        st->error = 30; st->done = 1; st->skip = 1;   // a peer never posted (failed / diverged): surface FNN_E_STATE
+                        return;
+                    }
+                }
+                double q; unsigned long long k;
+                mail_load_payload(ms, q, k);
+                if (better(q, k, bq, bk)) { bq = q; bk = k; }
+            }
         }
+        // the cluster the scan had masked, evaluated exactly by k_chain_patch
+        if (better(st->patchQ, st->patchKey, bq, bk)) { bq = st->patchQ; bk = st->patchKey; }
         st->selQ = bq;
         st->sel_i = (int)(bk >> 32);
         st->sel_j = (int)(bk & 0xffffffffu);
@@ -454,34 +314,58 @@ __device__ void select_body(const int* __restrict__ id, const int* __restrict__ 
     st->cy = cy; st->cyn = cy < P2 ? (cy ^ 1) : -1;
     st->need_rx = (st->cxn >= 0 || st->cyn >= 0);
     if (!strategy) st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
+    tl_stamp(st, TL_SEL1);
 }
 __global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
     if (st->done || threadIdx.x != 0) return;
     select_body(id, p2s, st, mail);
 }
 
-// ------------------------------------------------------------------ K3b: stage the ComputeRx operands on all SMs
-// rxs[r][k*1024 + t] = w_i * D[z_r][p_i] for position i = t*L + k (segment-transposed, so the summation block reads
-// coalesced); w = 1 for the four chosen nodes and singletons, 1/2 otherwise (NetMakerOriginal.java:555-558).
+// ------------------------------------------------------------------ K3b: ComputeRx operands on all SMs
+// For the <=4 rows z in {Cx, Cx.nbr, Cy, Cy.nbr}: term_i = w_i * D[z][p_i], w = 1 for the four chosen nodes and singletons,
+// 1/2 otherwise (NetMakerOriginal.java:555-558).  Two products:
+//   * rx_part[block][0..3] = this block's share of sum_i term_i, [4..7] = of sum_i |term_i| (any order: they only feed the
+//     certified pick of k_pick, which bounds the difference to the reference's left-to-right sum);
+//   * rxs[r][k*1024 + t] = term of position i = t*L + k (segment-transposed, so the exact summation block reads coalesced).
 __global__ void __launch_bounds__(256)
-k_rx_stage(const double* __restrict__ D, int64_t ld, const int* __restrict__ p2s, const DevState* st, double* __restrict__ rxs,
-           int64_t rxs_ld) {
+k_rx_stage(const double* __restrict__ D, int64_t ld, const int* __restrict__ pos, const DevState* st, double* __restrict__ rxs,
+           int64_t rxs_ld, double* __restrict__ rx_part) {
     if (st->done || !st->need_rx) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) tl_stamp(const_cast<DevState*>(st), TL_RX0);
     const int m = st->m, P2 = st->P2;
     const int Cx = st->cx, Cxn = st->cxn, Cy = st->cy, Cyn = st->cyn;
     const int L = (m + xsum::THREADS - 1) / xsum::THREADS;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        const int s = p2s[i];
+    const int zs[4] = {Cx, Cxn, Cy, Cyn};
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < m; s += gridDim.x * blockDim.x) {
+        const int i = pos[s];
         const bool full = (s >= P2) || s == Cx || s == Cxn || s == Cy || s == Cyn;
         const int64_t dst = (int64_t)(i % L) * xsum::THREADS + (i / L);
-        const int zs[4] = {Cx, Cxn, Cy, Cyn};
 #pragma unroll
         for (int r = 0; r < 4; ++r)
             if (zs[r] >= 0) {
                 const double v = D[(int64_t)zs[r] * ld + s];
-                rxs[(int64_t)r * rxs_ld + dst] = full ? v : v * 0.5;
+                const double t = full ? v : v * 0.5;
+                rxs[(int64_t)r * rxs_ld + dst] = t;
+                acc[r] += t;
+                acc[4 + r] += fabs(t);
             }
     }
+    __shared__ double wsum[8][8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        double v = acc[q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += wsum[w][threadIdx.x];
+        rx_part[blockIdx.x * 8 + threadIdx.x] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) tl_stamp(const_cast<DevState*>(st), TL_RX1);
 }
 
 // ------------------------------------------------------------------ K3: pick + bookkeeping (one block)
@@ -489,13 +373,16 @@ constexpr int PICK_THREADS = 1024;
 
 __global__ void __launch_bounds__(PICK_THREADS, 1)
 k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState* st, int* amalg, double* trace, int serial_chain,
-       const double* __restrict__ rxs, int64_t rxs_ld) {
+       const double* __restrict__ rxs, int64_t rxs_ld, const double* __restrict__ rx_part, int rx_blocks, int force_exact) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[4][CH_TILE] = reinterpret_cast<double (*)[4][CH_TILE]>(smem_raw);
     __shared__ double rx[4];
+    __shared__ double rxa[8];
+    __shared__ int s_exact, s_kstar;
     if (st->done) return;
     const int m = st->m, c = st->c, P2 = st->P2;
     const int tid = threadIdx.x;
+    if (tid == 0) tl_stamp(st, TL_PICK0);
 
     // ---- special case: 4 active nodes in 2 clusters (NetMakerOriginal.java:343-360)
     if (m == 4 && c == 2) {
@@ -529,8 +416,71 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
 
     const int Cx = st->cx, Cxn = st->cxn, Cy = st->cy, Cyn = st->cyn;   // k_select
 
+    // ---- warm this SM's L1 with the O(1) scalars the single control thread is about to chase one after another
+    // (the 4x4 distances among the chosen nodes, id/pos of the chosen and of the slots a layout move can touch)
+    if (tid >= 32 && tid < 96) {
+        const int k = tid - 32;
+        const int zs4[4] = {Cx, Cxn, Cy, Cyn};
+        const void* a = nullptr;
+        if (k < 16) { const int r = zs4[k >> 2], q = zs4[k & 3]; if (r >= 0 && q >= 0) a = D + (int64_t)r * ld + q; }
+        else if (k < 40) {
+            const int j = (k - 16) >> 1;   // 0..11
+            const int cand[12] = {Cx, Cxn, Cy, Cyn, m - 1, m - 2, P2 - 2, P2 - 1, P2, P2 + 1, m - 3, P2 - 4};
+            const int sl = cand[j];
+            if (sl >= 0 && sl < m) a = ((k & 1) ? (const void*)(pos + sl) : (const void*)(id + sl));
+        } else if (k < 43) { const int q = m - 1 - (k - 40); if (q >= 0) a = p2s + q; }
+        if (a) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    }
+
+    // ---- certified pick: the <=4 ComputeRx sums only decide which of the <=4 candidate pairs is joined (:428-452).
+    // R~ = sum of k_rx_stage's per-block partials (some order), A = the same over |terms|.  Any two summation orders of
+    // the same m terms differ by at most 2*gamma_m*A (gamma_m = m*u/(1-m*u), u = 2^-53), so with E = (2m+256)*u*A the
+    // reference's left-to-right sum lies in [R~-E, R~+E]; each candidate Q = (f*d - Ra) - Rb then lies within
+    // e = 1.01*(Ea+Eb) + 8u*(|f*d|+|Ra|+|Rb|) of its value computed from R~.  If the smallest candidate is separated
+    // from every other one by more than the two bounds, the exact sums would pick the same pair: no chain needed.
+    // Otherwise (near-ties, e.g. integer matrices), and whenever a trace is recorded (its `best` column is the exact
+    // value, and the certified decision is then cross-checked against it), the exact sums decide.
+    const bool need_rx = (Cxn >= 0 || Cyn >= 0);
+    if (need_rx) {
+        if (tid < 256) {   // warp w sums quantity w over the blocks
+            const int q = tid >> 5, lane = tid & 31;
+            double v = 0.0;
+            for (int b = lane; b < rx_blocks; b += 32) v += rx_part[b * 8 + q];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) rxa[q] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double U = 1.1102230246251565e-16;
+            const double f = (double)(c + (Cxn >= 0) + (Cyn >= 0)) - 2.0;
+            const int zs4[4] = {Cx, Cxn, Cy, Cyn};
+            const int ra[4] = {0, 1, 0, 1}, rb[4] = {2, 2, 3, 3};
+            double Q[4], e[4];
+            bool pres[4] = {true, Cxn >= 0, Cyn >= 0, Cxn >= 0 && Cyn >= 0};
+            bool finite = true;
+            int ks = 0;
+            for (int k = 0; k < 4; ++k) {
+                if (!pres[k]) continue;
+                const double Ra = rxa[ra[k]], Rb = rxa[rb[k]];
+                const double Ea = rxa[4 + ra[k]] * ((2.0 * (double)m + 256.0) * U), Eb = rxa[4 + rb[k]] * ((2.0 * (double)m + 256.0) * U);
+                const double t = f * D[(int64_t)zs4[ra[k]] * ld + zs4[rb[k]]];
+                Q[k] = (t - Ra) - Rb;
+                e[k] = 1.01 * (Ea + Eb) + 8.0 * U * (fabs(t) + fabs(Ra) + fabs(Rb));
+                finite = finite && isfinite(Q[k]) && isfinite(e[k]);
+                if (Q[k] < Q[ks]) ks = k;
+            }
+            bool cert = finite;
+            for (int k = 0; k < 4 && cert; ++k)
+                if (pres[k] && k != ks && !(Q[ks] + e[ks] < Q[k] - e[k])) cert = false;
+            s_kstar = cert ? ks : -1;
+            s_exact = (!cert || force_exact || trace != nullptr) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+
     // ---- ComputeRx x<=4 (:413-420, :549-561): sequential in position order
-    if (Cxn >= 0 || Cyn >= 0) {
+    if (need_rx && s_exact) {
         const int zs[4] = {Cx, Cxn, Cy, Cyn};
         const int L = (m + xsum::THREADS - 1) / xsum::THREADS;   // rxs is segment-transposed by k_rx_stage
         auto load_seg = [&](int r, int t, int k) -> double { return rxs[(int64_t)r * rxs_ld + (int64_t)k * xsum::THREADS + t]; };
@@ -546,13 +496,26 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
     // ================= single-thread control: everything below is O(1) =================
     auto d = [&](int a, int b) { return D[(int64_t)a * ld + b]; };
     int x = Cx, y = Cy;
-    {
+    if (need_rx && !s_exact) {
+        // certified: candidate order (Cx,Cy), (Cx.nbr,Cy), (Cx,Cy.nbr), (Cx.nbr,Cy.nbr)
+        const int ks = s_kstar;
+        x = (ks & 1) ? Cxn : Cx;
+        y = (ks & 2) ? Cyn : Cy;
+        st->cert_ok += 1;
+    } else {
         int mm = c + (Cxn >= 0) + (Cyn >= 0);
         const double f = (double)mm - 2.0;
+        int kx = 0;
         double best = (f * d(Cx, Cy) - rx[0]) - rx[2];
-        if (Cxn >= 0) { double q = (f * d(Cxn, Cy) - rx[1]) - rx[2]; if (q < best) { x = Cxn; y = Cy; best = q; } }
-        if (Cyn >= 0) { double q = (f * d(Cx, Cyn) - rx[0]) - rx[3]; if (q < best) { x = Cx; y = Cyn; best = q; } }
-        if (Cxn >= 0 && Cyn >= 0) { double q = (f * d(Cxn, Cyn) - rx[1]) - rx[3]; if (q < best) { x = Cxn; y = Cyn; best = q; } }
+        if (Cxn >= 0) { double q = (f * d(Cxn, Cy) - rx[1]) - rx[2]; if (q < best) { x = Cxn; y = Cy; best = q; kx = 1; } }
+        if (Cyn >= 0) { double q = (f * d(Cx, Cyn) - rx[0]) - rx[3]; if (q < best) { x = Cx; y = Cyn; best = q; kx = 2; } }
+        if (Cxn >= 0 && Cyn >= 0) { double q = (f * d(Cxn, Cyn) - rx[1]) - rx[3]; if (q < best) { x = Cxn; y = Cyn; best = q; kx = 3; } }
+        if (need_rx) {
+            if (s_kstar >= 0) {   // exact sums were computed although the pick was certifiable: cross-check the certificate
+                st->cert_ok += 1;
+                if (s_kstar != kx) { st->error = 21; st->done = 1; st->skip = 1; return; }
+            } else st->cert_fail += 1;
+        }
         if (trace) {
             double* tr = trace + 8 * (int64_t)st->iter;
             tr[0] = m; tr[1] = c; tr[2] = id[Cx]; tr[3] = id[Cy]; tr[4] = id[x]; tr[5] = id[y]; tr[7] = best;
@@ -647,6 +610,7 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
         p2s[cpos[k]] = cslot[k];
     }
     st->skip = 0;
+    tl_stamp(st, TL_PICK1);
 }
 
 // formula rows of the new nodes at old column a (bystander columns; order independent)
@@ -685,6 +649,7 @@ __device__ __forceinline__ double sub_dist(const double* D, int64_t ld, int p, b
 __global__ void __launch_bounds__(256)
 k_rows(const double* __restrict__ D, int64_t ld, double* Sx, DevState* st, double* scratch) {
     if (st->done || st->skip) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) tl_stamp(st, TL_ROWS0);
     const int m = st->m, P2 = st->P2, m_new = st->m_new, K = st->K;
     __shared__ int cslot[MAXK], csrc[MAXK];
     if (threadIdx.x < MAXK) { cslot[threadIdx.x] = st->chg_slot[threadIdx.x]; csrc[threadIdx.x] = st->chg_src[threadIdx.x]; }
@@ -734,13 +699,18 @@ k_rows(const double* __restrict__ D, int64_t ld, double* Sx, DevState* st, doubl
             }
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) tl_stamp(st, TL_ROWS1);
 }
 
 // ------------------------------------------------------------------ K5b+K6a: scatter rows/cols + add sweep
+// The last block to finish commits the iteration (m, c, P2, iter, done) and masks the new cluster for the next scan:
+// its u.Sx is summed by k_chain_patch concurrently with that scan.
 __global__ void __launch_bounds__(256)
 k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevState* st, const double* __restrict__ scratch,
-          double* stage) {
+          double* stage, const int* __restrict__ id, const int* __restrict__ p2s) {
     if (st->done || st->skip) return;
+    __shared__ bool amLast;
+    if (blockIdx.x == 0 && threadIdx.x == 0) tl_stamp(st, TL_SCAT0);
     const int m_new = st->m_new, P2n = st->P2_new, K = st->K, su = st->su;
     const int Ln = (m_new + xsum::THREADS - 1) / xsum::THREADS;   // stage is segment-transposed for k_chain
     auto sidx = [&](int p) -> int { return (p % Ln) * xsum::THREADS + p / Ln; };
@@ -777,30 +747,99 @@ k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevSta
         stage[sidx(pos[t])] = dpu;
         if (pPair) { Sx[t + 1] = base1 + dpu; stage[sidx(pos[t + 1])] = 0.0; }
     }
-}
-
-// ------------------------------------------------------------------ K6b: u.Sx chain + commit
-__global__ void __launch_bounds__(PICK_THREADS, 1)
-k_chain(double* Sx, const int* id, const int* p2s, DevState* st, const double* __restrict__ stage, int serial_chain) {
-    extern __shared__ unsigned char smem_raw[];
-    double (*buf)[1][CH_TILE] = reinterpret_cast<double (*)[1][CH_TILE]>(smem_raw);
-    __shared__ double tot[1];
-    if (st->done || st->skip) return;
-    const int m_new = st->m_new;
-    const int Ln = (m_new + xsum::THREADS - 1) / xsum::THREADS;
-    auto load_seg = [&](int, int t, int k) -> double { return stage[k * xsum::THREADS + t]; };
-    auto load_lin = [&](int, int i) -> double { return stage[(i % Ln) * xsum::THREADS + i / Ln]; };
-    if (serial_chain) block_seq_sum<1>(buf, m_new, load_lin, tot);
-    else xsum::block_exact_seq_sum<1>(reinterpret_cast<xsum::Smem*>(smem_raw), m_new, load_seg, [](int) { return true; }, tot);
-    if (threadIdx.x == 0) {
-        const int su = st->su;
-        Sx[su] = tot[0];
-        Sx[su + 1] = tot[0];
-        st->m = m_new; st->c = st->c_new; st->P2 = st->P2_new;
+    // ---- commit: every block has read the event descriptor before it arrives here
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) amLast = (atomicAdd(&st->commit_ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (amLast && threadIdx.x == 0) {
+        __threadfence();
+        st->commit_ticket = 0;
+        tl_stamp(st, TL_SCAT1);
+        st->m = m_new; st->c = st->c_new; st->P2 = P2n;
         st->iter += 1;
+        st->mask_su = su;
         if (m_new <= 3) {
             st->done = 1;
             for (int i = 0; i < 3; ++i) st->final3[i] = id[p2s[i]];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K6b: u.Sx chain + the new cluster's pairs
+// Runs on a forked graph branch, concurrently with the NEXT iteration's selection scan (which reads the new cluster's Sx
+// as -inf).  (1) u.Sx = left-to-right sum of Dpu in position order (NetMakerOriginal.java:530-535), bit-exact;
+// (2) Q of (u-cluster, every other cluster) with that exact u.Sx, in the reference's role order (:215-226), min-loc on the
+// same (Q, i, j) key as the scan; (3) single GPU, canonical: the second of {scan's last block, this block} to arrive merges
+// the two partial min-locs and decodes Cx, Cy.
+__global__ void __launch_bounds__(PICK_THREADS, 1)
+k_chain_patch(const double* __restrict__ D, int64_t ld, double* Sx, const int* __restrict__ id, const int* __restrict__ pos,
+              const int* __restrict__ p2s, DevState* st, const double* __restrict__ stage, int serial_chain, int fused_select) {
+    extern __shared__ unsigned char smem_raw[];
+    double (*buf)[1][CH_TILE] = reinterpret_cast<double (*)[1][CH_TILE]>(smem_raw);
+    __shared__ double tot[1];
+    __shared__ Partial wbest[PICK_THREADS / 32];
+    if (st->done) return;
+    const int tid = threadIdx.x;
+    const int su = st->mask_su;
+    const int m = st->m, P2 = st->P2;   // committed by k_scatter
+    const bool strategy = (st->mode != 0 && m > st->fallback);
+    double bq = INFINITY;
+    unsigned long long bk = ~0ull;
+    if (tid == 0) tl_stamp(st, TL_CHAIN0);
+    if (su >= 0) {
+        const int Ln = (m + xsum::THREADS - 1) / xsum::THREADS;
+        auto load_seg = [&](int, int t, int k) -> double { return stage[k * xsum::THREADS + t]; };
+        auto load_lin = [&](int, int i) -> double { return stage[(i % Ln) * xsum::THREADS + i / Ln]; };
+        if (serial_chain) block_seq_sum<1>(buf, m, load_lin, tot);
+        else xsum::block_exact_seq_sum<1>(reinterpret_cast<xsum::Smem*>(smem_raw), m, load_seg, [](int) { return true; }, tot);
+        const double Su = tot[0];
+        if (tid == 0) { Sx[su] = Su; Sx[su + 1] = Su; tl_stamp(st, TL_CHAIN1); }
+        if (!strategy && !(m == 4 && st->c == 2)) {
+            const double cm2 = (double)st->c - 2.0;
+            const int posU = pos[su];
+            const double* ru = D + (int64_t)su * ld;
+            const double* run = ru + ld;
+            for (int t = tid; t < m; t += PICK_THREADS) {
+                const bool tPair = t < P2;
+                if ((tPair && (t & 1)) || (t & ~1) == su) continue;   // representatives of the other clusters
+                const int pt = pos[t];
+                const double St = Sx[t];
+                const bool uIsP = posU > pt;   // the higher position plays p (:208-213)
+                double dpq;
+                if (tPair) {
+                    const double a = ru[t], b = run[t], c2 = ru[t + 1], d2 = run[t + 1];
+                    dpq = uIsP ? (((a + c2) + b) + d2) * 0.25 : (((a + b) + c2) + d2) * 0.25;
+                } else dpq = (ru[t] + run[t]) * 0.5;
+                const double q = uIsP ? (cm2 * dpq - Su) - St : (cm2 * dpq - St) - Su;
+                const unsigned long long key = uIsP ? (((unsigned long long)posU << 32) | (unsigned)pt)
+                                                    : (((unsigned long long)pt << 32) | (unsigned)posU);
+                if (better(q, key, bq, bk)) { bq = q; bk = key; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double oq = __shfl_down_sync(0xffffffffu, bq, off);
+                const unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, off);
+                if (better(oq, ok, bq, bk)) { bq = oq; bk = ok; }
+            }
+            if ((tid & 31) == 0) wbest[tid >> 5] = Partial{bq, bk};
+            __syncthreads();
+            if (tid == 0)
+                for (int w = 1; w < PICK_THREADS / 32; ++w)
+                    if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
+        }
+    }
+    if (tid == 0) {
+        st->patchQ = bq;
+        st->patchKey = bk;
+        tl_stamp(st, TL_PATCH1);
+        if (fused_select) {
+            __threadfence();
+            if (atomicAdd(&st->join_ticket, 1u) == 1u) {
+                __threadfence();
+                st->join_ticket = 0;
+                select_body(id, p2s, st, nullptr);
+            }
         }
     }
 }
@@ -844,9 +883,17 @@ struct fnn_ctx {
     int *id = nullptr, *pos = nullptr, *p2s = nullptr, *amalg = nullptr;
     DevState* st = nullptr;
     Partial* partials = nullptr;
+    double* rx_part = nullptr;        // per-block partial ComputeRx sums of k_rx_stage
     int scan_grid = 0, row_grid = 0;
-    // the scan's last block also decodes Cx, Cy (saves the k_select launch) when nothing has to be merged or overridden
-    bool fused_select() const { return have_tmap && world == 1 && o.mode == FNN_CANONICAL; }
+    // u.Sx chain + new-cluster patch on a forked branch, concurrent with the next scan (which then leaves one SM to it)
+    bool overlap = false;
+    int force_exact = 0;              // A/B: always decide the pick with the exact left-to-right sums
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool join_pending = false;        // a k_chain_patch has been issued on stream2 and not yet waited for
+    // the later of {scan's last block, k_chain_patch} also decodes Cx, Cy (saves the k_select launch) when nothing else
+    // has to be merged or overridden
+    bool fused_select() const { return world == 1 && o.mode == FNN_CANONICAL; }
     int launches_per_iter() const { return 6 + (fused_select() ? 0 : 1) + (o.mode >= FNN_RANDOM_N ? 2 : 0) + (o.mode == FNN_RELAXED ? 1 : 0); }
     DevState* h_st = nullptr;  // pinned
     CUtensorMap tmap;
@@ -859,6 +906,9 @@ struct fnn_ctx {
     void* opened[MAX_WORLD] = {nullptr};
     cudaGraphExec_t graph = nullptr;
     int graph_iters = 0;
+    unsigned long long* tl = nullptr;  // debug timeline (FNN_TIMELINE)
+    int tl_iter0 = 0, tl_count = 0;
+    std::string tl_path;
     bool loaded = false;
     fnn_stats stats{};
     int64_t trace_rows = 0;
@@ -908,7 +958,11 @@ extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
     cudaFree(c->mail); cudaFree(c->peers);
     cudaFree(c->nbrpos); cudaFree(c->pairs); cudaFree(c->walk); cudaFree(c->walk_ticket);
     cudaFree(c->id); cudaFree(c->pos); cudaFree(c->p2s); cudaFree(c->amalg); cudaFree(c->st); cudaFree(c->partials);
+    cudaFree(c->rx_part); cudaFree(c->tl);
     if (c->h_st) cudaFreeHost(c->h_st);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -968,9 +1022,12 @@ static int ctx_build(fnn_ctx* c, const fnn_opts* o, int64_t n) {
         pt.box[0] = c->mail;
         FNN_CUDA(cudaMemcpy(c->peers, &pt, sizeof(pt), cudaMemcpyHostToDevice));
     }
-    c->scan_grid = c->sms * 2;
-    c->row_grid = std::max<int>(1, std::min<int64_t>((n + 255) / 256, c->sms * 4));
-    FNN_ALLOC(c->partials, sizeof(Partial) * c->scan_grid);
+    c->overlap = (o->mode == FNN_CANONICAL) && !(o->reserved[5] & 1) && c->sms > 8;
+    c->force_exact = (o->reserved[5] & 2) ? 1 : 0;
+    c->scan_grid = c->sms - (c->overlap ? 1 : 0);
+    c->row_grid = std::max<int>(1, std::min<int64_t>((n + 255) / 256, std::min(c->sms * 4, RX_BLOCKS_MAX)));
+    FNN_ALLOC(c->partials, sizeof(Partial) * c->sms);
+    FNN_ALLOC(c->rx_part, sizeof(double) * 8 * RX_BLOCKS_MAX);
     if (o->record_trace) FNN_ALLOC(c->trace, sizeof(double) * 8 * (n + 8));
     if (o->mode == FNN_RELAXED) {
         c->rl_max_lists = (int)(2 * n + 16); c->rl_tie_cap = (int)(16 * n + 65536); c->rl_mymin_cap = (int)(8 * n + 65536);
@@ -992,16 +1049,25 @@ static int ctx_build(fnn_ctx* c, const fnn_opts* o, int64_t n) {
         FNN_ALLOC(c->walk_ticket, sizeof(unsigned int));
         FNN_CUDA(cudaMemset(c->walk_ticket, 0, sizeof(unsigned int)));
     }
+    if (const char* e = getenv("FNN_TIMELINE")) {   // "iter0,count,file": debugging aid, never on in production
+        int i0 = 0, cnt = 0;
+        char path[400];
+        if (sscanf(e, "%d,%d,%399s", &i0, &cnt, path) == 3 && cnt > 0 && cnt <= 100000) {
+            c->tl_iter0 = i0; c->tl_count = cnt; c->tl_path = path;
+            FNN_ALLOC(c->tl, sizeof(unsigned long long) * TL_EVENTS * cnt);
+            FNN_CUDA(cudaMemset(c->tl, 0, sizeof(unsigned long long) * TL_EVENTS * cnt));
+        }
+    }
     FNN_CUDA(cudaMallocHost((void**)&c->h_st, sizeof(DevState)));
     FNN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    FNN_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    FNN_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    FNN_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     FNN_CUDA(cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICK_SMEM));
-    FNN_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
-    c->scan_grid = std::max(c->scan_grid, c->sms);
-    if (o->reserved[0] == 0) {  // reserved[0] = 1 selects the register-tiled scan (A/B only)
-        int trc = make_tensor_map(c);
-        if (trc) return trc;
-        FNN_CUDA(cudaFuncSetAttribute(tma::k_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma::SMEM_BYTES));
-    }
+    FNN_CUDA(cudaFuncSetAttribute(k_chain_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
+    int trc = make_tensor_map(c);
+    if (trc) return trc;
+    FNN_CUDA(cudaFuncSetAttribute(tma::k_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma::SMEM_BYTES));
     return FNN_OK;
 }
 
@@ -1058,10 +1124,8 @@ extern "C" int fnn_ctx_matrix_ptr(fnn_ctx* c, double** dptr, int64_t* ld) {
 static_assert(PICK_THREADS == xsum::THREADS, "exact-sum block size");
 
 static inline void launch_scan(fnn_ctx* c) {
-    if (c->have_tmap)
-        tma::k_scan_tma<<<c->sms, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials, c->peers, c->id, c->p2s, c->fused_select() ? 1 : 0);
-    else
-        k_scan<32><<<c->scan_grid, SCAN_THREADS, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->partials);
+    tma::k_scan_tma<<<c->scan_grid, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials, c->peers,
+                                                                              c->id, c->p2s, c->fused_select() ? 1 : 0);
 }
 
 // 2-D tiled tensor map over the n x ld matrix: box = 256 columns x 8 rows, no swizzle, zero OOB fill
@@ -1084,7 +1148,10 @@ static int make_tensor_map(fnn_ctx* c) {
     c->have_tmap = true;
     return FNN_OK;
 }
+// everything of an iteration after the scan.  The previous iteration's k_chain_patch (forked branch) joins here: the
+// strategy kernels, the selection merge and the update all need the new cluster's exact Sx.
 static inline void launch_rest(fnn_ctx* c) {
+    if (c->join_pending) { cudaStreamWaitEvent(c->stream, c->ev_join, 0); c->join_pending = false; }
     if (c->o.mode >= FNN_RANDOM_N) {
         modes::k_random_walk<<<1, modes::THREADS, 0, c->stream>>>(c->pos, c->p2s, c->st, c->nbrpos, c->pairs, c->walk);
         modes::k_random_eval<<<c->sms * 2, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->p2s, c->st, c->pairs, c->walk, c->partials,
@@ -1094,14 +1161,25 @@ static inline void launch_rest(fnn_ctx* c) {
         modes::k_relaxed_select<<<1, modes::THREADS, sizeof(xsum::Smem), c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st,
                                                                                      c->rl_machine, (int)c->n);
     if (!c->fused_select()) k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail);
-    k_rx_stage<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->p2s, c->st, c->rxs, c->rxs_ld);
+    k_rx_stage<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->pos, c->st, c->rxs, c->rxs_ld, c->rx_part);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
-                                                    c->serial_chain, c->rxs, c->rxs_ld);
+                                                    c->serial_chain, c->rxs, c->rxs_ld, c->rx_part, c->row_grid, c->force_exact);
     k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
-    k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage);
-    k_chain<<<1, PICK_THREADS, CHAIN_SMEM, c->stream>>>(c->Sx, c->id, c->p2s, c->st, c->stage, c->serial_chain);
+    k_scatter<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->scratch, c->stage, c->id, c->p2s);
+    cudaStream_t cs = c->stream;
+    if (c->overlap) {
+        cudaEventRecord(c->ev_fork, c->stream);
+        cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
+        cs = c->stream2;
+    }
+    k_chain_patch<<<1, PICK_THREADS, CHAIN_SMEM, cs>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->stage, c->serial_chain,
+                                                      c->fused_select() ? 1 : 0);
+    if (c->overlap) { cudaEventRecord(c->ev_join, c->stream2); c->join_pending = true; }
 }
-
+// the forked branch has to be back on the main stream before a capture ends, before the state is read, before the next run
+static inline void join_branch(fnn_ctx* c) {
+    if (c->join_pending) { cudaStreamWaitEvent(c->stream, c->ev_join, 0); c->join_pending = false; }
+}
 
 // expandNodes (NetMakerOriginal.java:246-325) on the host from the amalgamation log
 static bool expand_order(int64_t n, const std::vector<int>& lg, int n_amalg, const int* final3, int32_t* ordering) {
@@ -1150,7 +1228,8 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     FNN_CUDA(cudaEventRecord(e0, c->stream));
     const int ni = (int)n;
     k_init_nodes<<<(ni + 255) / 256, 256, 0, c->stream>>>(ni, c->id, c->pos, c->p2s, c->st, c->o.mode, c->o.mult,
-                                                          c->o.canonical_fallback, (long long)c->o.seed, c->rank, c->world, (long long)(++c->run_counter) << 32);
+                                                          c->o.canonical_fallback, (long long)c->o.seed, c->rank, c->world, (long long)(++c->run_counter) << 32,
+                                                          c->tl, c->tl_iter0, c->tl_count);
     k_rowsum<<<(ni + 127) / 128, 128, 0, c->stream>>>(c->D, c->ld, ni, c->Sx, c->st);
     FNN_CUDA(cudaGetLastError());
     int64_t launches = 2, scans = 0;
@@ -1179,6 +1258,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
         for (int64_t it = 0; it < max_iters; ++it) {
             const bool sample = (it % c->o.profile_every) == 0;
             if (sample) {
+                join_branch(c);
                 FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
                 FNN_CUDA(cudaStreamSynchronize(c->stream));
                 if (c->h_st->done) break;
@@ -1198,13 +1278,15 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
             launch_rest(c);
             launches += c->launches_per_iter(); ++scans;
         }
+        join_branch(c);
         FNN_CUDA(cudaGetLastError());
     } else if (c->o.use_graph) {
-        constexpr int GI = 16;  // iterations per graph
+        constexpr int GI = 32;  // iterations per graph
         if (!c->graph) {
             cudaGraph_t g;
             FNN_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             for (int i = 0; i < GI; ++i) { launch_scan(c); launch_rest(c); }
+            join_branch(c);
             FNN_CUDA(cudaStreamEndCapture(c->stream, &g));
             FNN_CUDA(cudaGraphInstantiate(&c->graph, g, 0));
             cudaGraphDestroy(g);
@@ -1228,18 +1310,43 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
                 launch_scan(c); launch_rest(c);
                 launches += c->launches_per_iter(); ++scans;
             }
+            join_branch(c);
             FNN_CUDA(cudaGetLastError());
             FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
             FNN_CUDA(cudaStreamSynchronize(c->stream));
             if (c->h_st->done) break;
         }
     }
+    join_branch(c);
     FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
     FNN_CUDA(cudaEventRecord(e1, c->stream));
     FNN_CUDA(cudaStreamSynchronize(c->stream));
+    FNN_CUDA(cudaStreamSynchronize(c->stream2));
     FNN_CUDA(cudaGetLastError());
-    if (c->h_st->error) { fnn::set_error("device-side selection strategy failed (code %d: 11/13 = tie or list pool overflow, 12 = candidate pool overflow, 10 = no pair found)", c->h_st->error); return FNN_E_STATE; }
+    if (c->h_st->error) {
+        fnn::set_error("device-side failure, code %d (10 = no pair found, 11/13 = tie or list pool overflow, 12 = candidate pool overflow, "
+                       "21 = certified pick disagrees with the exact sums, 30 = a peer rank never posted its partial min-loc)", c->h_st->error);
+        return FNN_E_STATE;
+    }
     if (!c->h_st->done) { fnn::set_error("agglomeration did not terminate (m=%d after %d iterations)", c->h_st->m, c->h_st->iter); return FNN_E_STATE; }
+    if (c->tl) {   // dump the timeline window (ns since its first stamp)
+        std::vector<unsigned long long> h((size_t)TL_EVENTS * c->tl_count);
+        FNN_CUDA(cudaMemcpy(h.data(), c->tl, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(c->tl_path.c_str(), "w")) {
+            fprintf(f, "iter,scan0,scan1,rx0,rx1,pick0,pick1,rows0,rows1,scat0,scat1,chain0,chain1,patch1,sel0,sel1\n");
+            unsigned long long base = 0;
+            for (size_t i = 0; i < h.size() && !base; ++i) base = h[i];
+            for (int k = 0; k < c->tl_count; ++k) {
+                fprintf(f, "%d", c->tl_iter0 + k);
+                for (int e = 0; e < 15; ++e) {
+                    const unsigned long long v = h[(size_t)k * TL_EVENTS + e];
+                    fprintf(f, ",%lld", v ? (long long)(v - base) : -1ll);
+                }
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     const int n_amalg = c->h_st->n_amalg;
     std::vector<int> lg(5 * (size_t)std::max(n_amalg, 1));
     FNN_CUDA(cudaMemcpy(lg.data(), c->amalg, sizeof(int) * 5 * n_amalg, cudaMemcpyDeviceToHost));
@@ -1257,6 +1364,10 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     c->stats.prof_scan_ms = prof_ms;
     c->stats.prof_scan_bytes = prof_bytes;
     c->stats.prof_scan_samples = prof_samples;
+    c->stats.reserved[0] = (double)c->h_st->cert_ok;     // picks decided by the bounded parallel ComputeRx sums
+    c->stats.reserved[1] = (double)c->h_st->cert_fail;   // picks that needed the exact left-to-right sums
+    c->stats.reserved[2] = (double)c->h_st->strat_bytes; // Relaxed row scans / Random samples: algorithmic bytes
+    c->stats.reserved[3] = (double)c->h_st->strat_units; // ... and their number
     c->trace_rows = c->h_st->iter;
     return FNN_OK;
 }
@@ -1343,7 +1454,6 @@ extern "C" int fnn_ctx_connect(fnn_ctx* c, int32_t rank, int32_t world, const vo
         fnn::set_error("fnn_ctx_connect: need 0 <= rank < world <= %d", MAX_WORLD);
         return FNN_E_ARG;
     }
-    if (!c->have_tmap) { fnn::set_error("fnn_ctx_connect: the sharded scan needs the TMA selection kernel"); return FNN_E_UNSUPPORTED; }
     FNN_CUDA(cudaSetDevice(c->o.device));
     for (int r = 0; r < MAX_WORLD; ++r)   // a second connect replaces the first wiring
         if (c->opened[r]) { cudaIpcCloseMemHandle(c->opened[r]); c->opened[r] = nullptr; }

@@ -211,8 +211,12 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
     const double cm2 = (double)st->c - 2.0;
     const int tid = threadIdx.x;
     const int ew = effective_world(st->world, m);   // ranks that share this scan (1: every rank scans all tiles)
+    // the cluster created by the previous iteration: its u.Sx is still being summed by k_chain_patch on a forked
+    // branch, which also evaluates that cluster's pairs exactly; here its Sx reads as -inf, i.e. Q = +inf
+    const int msk = st->mask_su;
 
     if (tid == 0) {
+        if (blockIdx.x == 0) tl_stamp(st, TL_SCAN0);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -258,7 +262,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
             it.decode(r0, cb0);
             const int rEnd = min(r0 + TILE_ROWS, m);
             if (tid < TILE_ROWS && r0 + tid < m) {   // stage the tile's row data
-                rowdata[tileParity][tid].S = Sx[r0 + tid];
+                rowdata[tileParity][tid].S = (((r0 + tid) & ~1) == msk) ? -INFINITY : Sx[r0 + tid];
                 rowdata[tileParity][tid].pos = pos[r0 + tid];
             }
             const int c0 = cb0 + box * BOX_W + lc;
@@ -269,6 +273,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
             if (cvalid) {
                 cS0 = Sx[c0]; cP0 = pos[c0];
                 if (c0 + 1 < m) { cS1 = Sx[c0 + 1]; cP1 = pos[c0 + 1]; }
+                if (c0 == msk) { cS0 = -INFINITY; cS1 = -INFINITY; }   // c0 is even, a masked pair is one thread's columns
             }
             asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
 
@@ -382,21 +387,30 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
             for (int w = 1; w < THREADS / 32; ++w)
                 if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
             st->ticket = 0;
+            tl_stamp(st, TL_SCAN1);
             if (ew > 1) {
                 // post this rank's partial into every rank's mailbox (own included); k_select merges
                 const int par = st->iter & 1;
                 const long long tag = st->run_tag + (long long)st->iter + 1;
                 for (int r = 0; r < st->world; ++r) {
                     MailSlot* ms = &peers->box[r]->slot[par][st->rank];
-                    mail_store(&ms->q, (unsigned long long)__double_as_longlong(bq), tag);
-                    mail_store(&ms->key, bk, tag);
+                    mail_store_payload(ms, bq, bk);
                 }
-                __threadfence_system();
+                __threadfence_system();   // payload before tag, system scope
+                for (int r = 0; r < st->world; ++r) mail_store_tag(&peers->box[r]->slot[par][st->rank], tag);
             } else {
-                st->selQ = bq;
-                st->sel_i = (int)(bk >> 32);
-                st->sel_j = (int)(bk & 0xffffffffu);
-                if (fused_select) select_body(ids, p2s, st, nullptr);   // Cx, Cy, id-order swap: saves a launch
+                st->scanQ = bq;
+                st->scanKey = bk;
+                // single GPU, canonical: whichever of {this block, k_chain_patch} arrives second merges the two partial
+                // min-locs and decodes Cx, Cy (saves the k_select launch); otherwise k_select does it after the join
+                if (fused_select) {
+                    __threadfence();
+                    if (atomicAdd(&st->join_ticket, 1u) == 1u) {
+                        __threadfence();
+                        st->join_ticket = 0;
+                        select_body(ids, p2s, st, nullptr);
+                    }
+                }
             }
         }
     }

@@ -53,8 +53,11 @@ typedef struct fnn_opts {
     int32_t use_graph;          /* 1: replay the per-iteration kernel sequence as a CUDA graph */
     int32_t record_trace;       /* 1: keep the per-iteration (m,c,Cx,Cy,x,y,kind,best) trace on device */
     int32_t profile_every;      /* >0: time the selection kernel of every k-th iteration with CUDA events */
-    int32_t reserved[6];        /* [0]=1: register-tiled scan instead of the TMA pipeline (A/B); [1]=1: sum the
-                                   sequential chains on one lane instead of the collapsed exact summation (A/B) */
+    int32_t reserved[6];        /* A/B switches, 0 = production: [1]=1: sum the sequential chains on one lane instead of the
+                                   collapsed exact summation; [3]=1: split weights = unconstrained closed form only;
+                                   [4]: split-weight solver variant (see fnn_split_weights); [5] bit 0: u.Sx chain on the
+                                   critical path instead of the forked branch, bit 1: always decide the 4-candidate pick
+                                   with the exact left-to-right ComputeRx sums (no certified parallel sums) */
 } fnn_opts;
 
 typedef struct fnn_ctx fnn_ctx; /* opaque: device matrix + node tables for one problem of n taxa */
@@ -69,7 +72,8 @@ typedef struct fnn_stats {
     int64_t prof_scan_samples;
     double order_ms;           /* device time of the whole ordering run (CUDA events) */
     double h2d_ms;             /* device time of the host->device matrix upload, if any */
-    double reserved[8];
+    double reserved[8];        /* [0] 4-candidate picks decided by the certified parallel ComputeRx sums, [1] picks that
+                                  needed the exact left-to-right sums (NetMakerOriginal.java:413-452) */
 } fnn_stats;
 
 void fnn_default_opts(fnn_opts* o);
@@ -111,6 +115,9 @@ int fnn_ctx_connect(fnn_ctx* c, int32_t rank, int32_t world, const void* handles
  * (host, n*n) or phylip_path must be non-NULL.  n<=3 returns the identity ordering
  * (NetMakerOriginal.java:133-140). */
 int fnn_order(const fnn_opts* o, const double* D_rowmajor, const char* phylip_path, int64_t n, int32_t* ordering_out);
+/* fnn_order keeps its last context (device buffers, tensor map, instantiated CUDA graph) for the next call with the same n
+ * and options; this releases it (the JNI shim calls it from JNI_OnUnload). */
+void fnn_release_cache(void);
 
 /* initial cluster row sums only (NetMakerOriginal.initialize, :164-191) — kernel K1, exposed for parity tests */
 int fnn_rowsums(const fnn_opts* o, const double* D_rowmajor, int64_t n, double* Sx_out);

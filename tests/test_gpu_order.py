@@ -54,6 +54,40 @@ def test_n3000(fnn):
     assert st["iterations"] >= 2997
 
 
+@pytest.mark.parametrize("opts", [{}, {"no_overlap": 1}, {"force_exact_pick": 1}, {"serial_chain": 1}, {"use_graph": 0}])
+def test_production_path_without_trace(fnn, opts):
+    """No trace recorded = the production configuration: the 4-candidate pick is decided by the certified parallel sums
+    (exact left-to-right sums only on near-ties) and u.Sx is summed on the forked branch while the next scan runs with
+    the new cluster masked.  The ordering must still be the oracle's, with every A/B switch."""
+    for D in (tree_matrix(2500, 8, 0.05), random_matrix(1300, 3), integer_matrix(900, 5, hi=4)):
+        o_ref, _, _ = oracle.order(D, want_trace=False)
+        with fnn.Context(D.shape[0], **opts) as c:
+            c.load_host(D)
+            o = c.order()
+            st = c.stats()
+        assert (o == o_ref).all()
+        if not opts.get("force_exact_pick"):
+            assert st["picks_certified"] > 0
+
+
+def test_certified_pick_statistics(fnn):
+    """Generic data: (almost) every pick is certified; integer matrices: exact ties force the exact sums."""
+    with fnn.Context(3000) as c:
+        c.load_host(tree_matrix(3000, 3, 0.05))
+        c.order()
+        st = c.stats()
+    assert st["picks_certified"] >= 0.99 * (st["picks_certified"] + st["picks_exact"])
+    # a constant matrix ties every candidate exactly: the certificate must refuse and the exact sums decide
+    D = np.ones((300, 300)) - np.eye(300)
+    o_ref, _, _ = oracle.order(D, want_trace=False)
+    with fnn.Context(300) as c:
+        c.load_host(D)
+        o = c.order()
+        st2 = c.stats()
+    assert (o == o_ref).all()
+    assert st2["picks_exact"] > 0 and st2["picks_certified"] == 0
+
+
 def test_rowsums(fnn):
     D = tree_matrix(777, 5)
     assert (fnn.rowsums(D) == oracle.rowsums(D)).all()
