@@ -129,8 +129,8 @@ def device_count():
 
 
 # A/B switches carried in fnn_opts.reserved (include/fastnn.h): name -> (index, bit or None for "whole int")
-_RESERVED = {"serial_chain": (1, None), "no_overlap": (5, 1), "force_exact_pick": (5, 2), "csw_graph_path": (4, None),
-             "csw_literal_order": (4, None)}
+_RESERVED = {"serial_chain": (1, None), "no_overlap": (5, 1), "force_exact_pick": (5, 2), "csw_variant": (4, None)}
+CSW_VARIANTS = {"default": 0, "graph": 1, "literal": 2}
 
 
 def default_opts(**kw):
@@ -287,9 +287,12 @@ def seq_sum(rows, serial=False, **opts):
     return out
 
 
-def split_weights(ordering, d_upper, constrained=True, **opts):
+def split_weights(ordering, d_upper, constrained=True, variant="default", **opts):
     """Seam B2 (fnn_split_weights): CircularSplitWeights.getWeights(ntax, ordering, d, v="ols", constrained, ...)
-    (CircularSplitWeights.java:162).  Returns (x[npairs] in the live split indexing, stats dict)."""
+    (CircularSplitWeights.java:162).  Returns (x[npairs] in the live split indexing, stats dict).
+    variant: "default" (production formulation), "graph" (launch-per-phase A/B path), "literal" (the reference's own
+    operation order on the device, n <= 512: the validation mode held bit for bit against the literal oracle)."""
+    opts = dict(opts, csw_variant=CSW_VARIANTS[variant])
     ordering = np.ascontiguousarray(ordering, dtype=np.int32)
     n = ordering.shape[0] - 1
     d_upper = np.ascontiguousarray(d_upper, dtype=np.float64)
@@ -379,8 +382,9 @@ def network(D, cutoff=1e-6, **opts):
     return ordering, si[:k].copy(), sj[:k].copy(), w[:k].copy()
 
 
-def csw_matvec(which, v, n, **opts):
+def csw_matvec(which, v, n, variant="default", **opts):
     """which: 'ab' | 'atx' | 'unconstrained' on a packed npairs vector (fnn_csw_matvec)."""
+    opts = dict(opts, csw_variant=CSW_VARIANTS[variant])
     v = np.ascontiguousarray(v, dtype=np.float64)
     o = default_opts(**opts)
     out = np.zeros_like(v)

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include "fastnn.h"
 #include "fnn_common.h"
+#include "fnn_exact_sum.cuh"
 
 namespace {
 
@@ -385,6 +386,132 @@ __global__ void k_setup_d(const double* __restrict__ d_upper, const int* __restr
     }
 }
 
+
+// ============================================================================ literal-order path (parity ladder L0 on the device)
+// opts.reserved[4] = 2.  The SAME arithmetic as CircularSplitWeights.java in the SAME order, so that the weights can be held
+// bit for bit against the literal CPU restatement (oracle/nnet_oracle.cpp) - the check the production formulation above
+// cannot give, because the active-set path is sensitive to summation order:
+//   * calculateAb / calculateAtx as the reference's n-1 dependent diagonals (:603-633, :643-731): one CTA, one
+//     __syncthreads per diagonal, each entry from the same three neighbours with the same operator order;
+//   * rowsum (:571-591) one thread per row, strictly in index order;
+//   * norm (:740-749) and the alpha dot (:815-817) as LEFT-TO-RIGHT sums, by the verified binade-collapsed exact
+//     summation of fnn_exact_sum.cuh (bit-identical to `for (k) ss += x[k]*x[k]` for any signs);
+//   * the whole loop of circularConjugateGrads (:769-831) in one single-CTA kernel.
+// A validation mode: n <= 512 (one exact-summation block covers n(n-1)/2 <= 131072 addends), O(n) barriers per mat-vec.
+namespace lit {
+constexpr int THREADS = xsum::THREADS;
+constexpr int MAX_N = 512;
+
+__device__ double rowsum(int n, const double* d, int k) {   // :571-591
+    double r = 0;
+    int64_t index = 0;
+    if (k > 0) {
+        index = k - 1;
+        for (int i = 0; i < k; i++) { r += d[index]; index += (n - i - 2); }
+        index++;
+    }
+    for (int j = k + 1; j < n; j++) r += d[index++];
+    return r;
+}
+// p = A^T d (:603-633); block-wide, p must not alias d
+__device__ void atx(int n, const double* d, double* p) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n - 1; i += THREADS) p[row_start(n, i)] = rowsum(n, d, i + 1);
+    __syncthreads();
+    for (int i = tid; i < n - 2; i += THREADS) {
+        const int64_t index = row_start(n, i) + 1;
+        p[index] = p[index - 1] + p[index + (n - i - 2)] - 2 * d[index + (n - i - 2)];
+    }
+    __syncthreads();
+    for (int k = 3; k <= n - 1; k++) {
+        for (int i = tid; i <= n - k - 1; i += THREADS) {
+            const int64_t index = row_start(n, i) + (k - 1);
+            p[index] = p[index - 1] + p[index + n - i - 2] - p[index + n - i - 3] - 2.0 * d[index + n - i - 2];
+        }
+        __syncthreads();
+    }
+}
+// d = A b (:643-731); block-wide, d must not alias b
+__device__ void ab(int n, const double* b, double* d) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= n - 2; i += THREADS) {
+        double d_ij = 0.0;
+        int64_t index = i - 1;
+        for (int k = 0; k <= i - 1; k++) { d_ij += b[index]; index += (n - k - 2); }
+        index++;
+        for (int k = i + 1; k <= n - 1; k++) d_ij += b[index++];
+        d[row_start(n, i)] = d_ij;
+    }
+    __syncthreads();
+    for (int i = tid; i <= n - 3; i += THREADS) {
+        const int64_t index = row_start(n, i) + 1;
+        d[index] = d[index - 1] + d[index + (n - i - 2)] - 2 * b[index - 1];
+    }
+    __syncthreads();
+    for (int k = 3; k <= n - 1; k++) {
+        for (int i = tid; i <= n - k - 1; i += THREADS) {
+            const int64_t index = row_start(n, i) + (k - 1);
+            d[index] = d[index - 1] + d[index + (n - i - 2)] - d[index + (n - i - 2) - 1] - 2.0 * b[index - 1];
+        }
+        __syncthreads();
+    }
+}
+// sum_k f(k), k = 0..len-1, strictly left to right; result to every thread
+template <typename F>
+__device__ double seqsum(xsum::Smem* sm, int len, F f, double* res) {
+    const int L = (len + xsum::THREADS - 1) / xsum::THREADS;
+    auto load = [&](int, int t, int k) -> double { return f(t * L + k); };
+    xsum::block_exact_seq_sum<1>(sm, len, load, [](int) { return true; }, res);
+    __syncthreads();
+    const double v = res[0];
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_matvec(int which, int n, const double* in, double* out) {
+    if (which == 0) ab(n, in, out); else atx(n, in, out);
+}
+
+// circularConjugateGrads (:769-831), W == 1; one CTA runs the whole loop
+__global__ void __launch_bounds__(THREADS, 1)
+k_cg(int n, int np, double* r, double* w, double* p, double* y, const double* b, const unsigned char* active, double* x,
+     Scalars* sc) {
+    extern __shared__ unsigned char smem_raw[];
+    xsum::Smem* sm = reinterpret_cast<xsum::Smem*>(smem_raw);
+    __shared__ double res[1];
+    const int tid = threadIdx.x;
+    const long long kmax = (long long)n * (n - 1) / 2;
+    ab(n, x, y);
+    atx(n, y, r);
+    for (int k = tid; k < np; k += THREADS) r[k] = active[k] ? 0.0 : b[k] - r[k];
+    __syncthreads();
+    double rho = seqsum(sm, np, [&](int k) { const double v = r[k]; return v * v; }, res);
+    double rho_old = 0;
+    const double e_0 = 1e-8 * sqrt(seqsum(sm, np, [&](int k) { const double v = b[k]; return v * v; }, res));
+    long long k = 0;
+    while ((rho > e_0 * e_0) && (k < kmax)) {
+        k = k + 1;
+        if (k == 1) { for (int i = tid; i < np; i += THREADS) p[i] = r[i]; }
+        else {
+            const double beta = rho / rho_old;
+            for (int i = tid; i < np; i += THREADS) p[i] = r[i] + beta * p[i];
+        }
+        __syncthreads();
+        ab(n, p, y);
+        atx(n, y, w);
+        for (int i = tid; i < np; i += THREADS) if (active[i]) w[i] = 0.0;
+        __syncthreads();
+        double alpha = seqsum(sm, np, [&](int i) { return p[i] * w[i]; }, res);
+        alpha = rho / alpha;
+        for (int i = tid; i < np; i += THREADS) { x[i] += alpha * p[i]; r[i] -= alpha * w[i]; }
+        __syncthreads();
+        rho_old = rho;
+        rho = seqsum(sm, np, [&](int i) { const double v = r[i]; return v * v; }, res);
+    }
+    if (tid == 0) { sc->iters_total += k; sc->k = k; sc->rho = rho; sc->done = 1; }
+}
+}  // namespace lit
+
 // ============================================================================ host driver
 struct Csw {
     int n = 0;
@@ -399,6 +526,7 @@ struct Csw {
     Scalars* h_sc = nullptr;
     cudaGraphExec_t cg_graph = nullptr;
     int64_t cg_calls = 0, outer = 0, inner = 0, launches = 0, launches_per_graph = 0;
+    int literal = 0;           // opts.reserved[4] == 2: the reference's own operation order (namespace lit), n <= 512
     // cub scratch and the 60 % collapse work arrays
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
@@ -450,6 +578,7 @@ struct Csw {
     }
     // out = A in   (d = A b)
     void Ab(const double* in, double* out, const int* gate) {
+        if (literal) { lit::k_matvec<<<1, lit::THREADS, 0, st>>>(0, n, in, out); launches += 1; return; }
         k_rowscan<<<std::min(n, 148 * 8), 256, 0, st>>>(in, Rw, nullptr, n, gate);
         colscan<false>(in, gate);
         k_ab_combine<<<grid_rows(), 256, 0, st>>>(P, out, n, gate);
@@ -463,6 +592,7 @@ struct Csw {
         launches += 5;
     }
     void Atx(const double* in, double* out, const int* gate) {
+        if (literal) { lit::k_matvec<<<1, lit::THREADS, 0, st>>>(1, n, in, out); launches += 1; return; }
         Atx_prefix(in, gate);
         k_atx_combine<0><<<(unsigned)nblk, 256, 0, st>>>(P, PRS, out, n, np, nullptr, nullptr, nullptr, gate);
         launches += 1;
@@ -497,6 +627,12 @@ struct Csw {
         h_sc->k = 0;
         FNN_CUDA(cudaMemsetAsync(&sc->done, 0, sizeof(int), st));
         FNN_CUDA(cudaMemsetAsync(&sc->k, 0, sizeof(long long), st));
+        if (literal) {
+            lit::k_cg<<<1, lit::THREADS, sizeof(xsum::Smem), st>>>(n, (int)np, r, w, p, y, AtWd, active, x, sc);
+            launches += 1;
+            FNN_CUDA(cudaGetLastError());
+            return FNN_OK;
+        }
         Ab(x, y, nullptr);
         Atx(y, r, nullptr);
         k_residual_init<<<(unsigned)nblk, 256, 0, st>>>(r, AtWd, active, np, part1);
@@ -603,9 +739,11 @@ static int active_conjugate(Csw& c) {
     k_fill<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.old_x, c.np, 1.0);
     FNN_CUDA(cudaMemsetAsync(c.active, 0, c.np, c.st));
     c.Atx(c.d, c.AtWd, nullptr);   // y = W*d = d
-    // e_0 depends only on b = AtWd: compute once
-    k_square_partials<<<(unsigned)c.nblk, 256, 0, c.st>>>(c.AtWd, c.np, c.part1);
-    c.finish_tree(EP_E0, 0);
+    // e_0 depends only on b = AtWd: compute once (the literal path recomputes it, left to right, in lit::k_cg)
+    if (!c.literal) {
+        k_square_partials<<<(unsigned)c.nblk, 256, 0, c.st>>>(c.AtWd, c.np, c.part1);
+        c.finish_tree(EP_E0, 0);
+    }
     FNN_CUDA(cudaMemcpyAsync(&c.sc->kmax, &c.np, sizeof(long long), cudaMemcpyHostToDevice, c.st));
     bool first_pass = true;
     while (true) {
@@ -641,6 +779,8 @@ extern "C" int fnn_csw_matvec(const fnn_opts* o, int32_t which, const double* v,
     FNN_CUDA(cudaSetDevice(o ? o->device : 0));
     Csw c;
     c.n = (int)n; c.np = n * (n - 1) / 2; c.nblk = (c.np + 1023) / 1024;
+    c.literal = (o && o->reserved[4] == 2) ? 1 : 0;
+    if (c.literal && n > lit::MAX_N) { fnn::set_error("fnn_csw_matvec: the literal-order validation mode covers n <= %d", lit::MAX_N); return FNN_E_ARG; }
     int rc = c.alloc();
     if (!rc) {
         cudaMemcpyAsync(c.x, v, sizeof(double) * c.np, cudaMemcpyHostToDevice, c.st);
@@ -661,8 +801,11 @@ extern "C" int fnn_csw_matvec(const fnn_opts* o, int32_t which, const double* v,
 static int solve_split_weights(Csw& c, const fnn_opts* o, const int32_t* ordering, const double* d_upper, int64_t n,
                                bool d_upper_on_device = false) {
     c.n = (int)n; c.np = n * (n - 1) / 2; c.nblk = (c.np + 1023) / 1024;
+    c.literal = (o && o->reserved[4] == 2) ? 1 : 0;
+    if (c.literal && n > lit::MAX_N) { fnn::set_error("split weights: the literal-order validation mode covers n <= %d", lit::MAX_N); return FNN_E_ARG; }
     int rc = c.alloc();
     if (rc) return rc;
+    if (c.literal) FNN_CUDA(cudaFuncSetAttribute(lit::k_cg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(xsum::Smem)));
     int* d_ord = reinterpret_cast<int*>(c.tie_rank);   // scratch: free until the first 60 % collapse
     FNN_CUDA(cudaMemcpyAsync(d_ord, ordering, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c.st));
     FNN_CUDA(cudaMemcpyAsync(c.r, d_upper, sizeof(double) * c.np, d_upper_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,

@@ -78,13 +78,13 @@ struct DevState {
     int rank, world;
     long long run_tag;            // (run counter << 32): makes mailbox tags unique across runs of one context
     int pick_x_id, pick_y_id, pick_kind;
-    int cx, cxn, cy, cyn, need_rx;   // k_select: chosen clusters (slots) and whether ComputeRx is needed
+    int cx, cxn, cy, cyn, need_rx;   // k_rx_stage: chosen clusters (slots) and whether ComputeRx is needed
     unsigned long long rng;       // java.util.Random state (48 bits)
     double Dmax;                  // max |D| at load time (slack of the scan's filter, fnn_scan_tma.cuh)
     double alg_bytes;             // running sum of the selection scan's algorithmic bytes
     // ---- chain off the critical path: the cluster created by the previous iteration is masked in the scan
     int mask_su;                  // base slot of the cluster whose u.Sx is still being summed (-1: none)
-    unsigned int join_ticket;     // scan's last block and k_chain_patch: the second to arrive merges and selects
+    unsigned int pad2;
     unsigned int commit_ticket;   // k_scatter: the last block to finish commits (m, c, P2, iter, done)
     int pad1;
     double scanQ, patchQ;         // partial min-locs: the masked scan / the new cluster's rows
@@ -122,8 +122,8 @@ __device__ __forceinline__ void mail_store_payload(MailSlot* ms, double q, unsig
     asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(&ms->q), "d"(q) : "memory");
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(&ms->key), "l"(key) : "memory");
 }
-__device__ __forceinline__ void mail_store_tag(MailSlot* ms, long long tag) {
-    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(&ms->tag), "l"(tag) : "memory");
+__device__ __forceinline__ void mail_store_tag(MailSlot* ms, long long tag) {   // after a __threadfence_system()
+    asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(&ms->tag), "l"(tag) : "memory");
 }
 __device__ __forceinline__ long long mail_load_tag(const MailSlot* ms) {
     long long t;
@@ -159,7 +159,6 @@ __device__ __forceinline__ bool better(double q, unsigned long long k, double bq
 }  // namespace
 #include <cuda.h>
 namespace {
-__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail);
 #include "fnn_scan_tma.cuh"
 #include "fnn_exact_sum.cuh"
 #include "fnn_modes.cuh"
@@ -176,7 +175,6 @@ __global__ void k_init_nodes(int n, int* id, int* pos, int* p2s, DevState* st, i
         st->rank = rank; st->world = world; st->run_tag = run_tag;
         st->rng = ((unsigned long long)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);   // java.util.Random(seed)
         st->mask_su = -1;
-        st->join_ticket = 1;   // no k_chain_patch precedes the first scan: its arrival is pre-paid
         st->patchQ = INFINITY; st->patchKey = ~0ull;
         st->scanQ = INFINITY; st->scanKey = ~0ull;
         st->tl = tl; st->tl_iter0 = tl_iter0; st->tl_count = tl_count;
@@ -270,55 +268,47 @@ __device__ __forceinline__ double duv_rule(bool uFirst, double dZX, double dYX, 
     return TWO_THIRDS * B + dYX / 3.0;
 }
 
-// ------------------------------------------------------------------ K3a: selection result -> clusters (one warp)
-// Multi-GPU: merges the per-rank partial min-locs posted by every rank's scan.  Then Cx, Cy from the
-// (i, j) key (or from the Relaxed/Random strategy), the id-order swap of NetMakerOriginal.java:376-380.
-__device__ void select_body(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
+// ------------------------------------------------------------------ K3a: selection result -> clusters
+// Computed redundantly by one thread of EVERY block of k_rx_stage (a handful of dependent L2 loads), so that it costs no
+// launch, no ticket and no fence: merge the partial min-locs - the masked scan's (single GPU) or every rank's, posted
+// into this rank's mailbox over NVLink (multi-GPU) - with k_chain_patch's partial for the masked cluster; then Cx, Cy from
+// the (i, j) key (or from the Relaxed/Random strategy) and the id-order swap of NetMakerOriginal.java:376-380.
+struct Sel { int cx, cxn, cy, cyn, need_rx, ok; double q; int i, j; };
+__device__ Sel select_decode(const int* __restrict__ id, const int* __restrict__ p2s, const DevState* st, const Mailbox* mail) {
+    Sel r{-1, -1, -1, -1, 0, 1, 0.0, 0, 0};
     const int m = st->m, P2 = st->P2;
-    if (m == 4 && st->c == 2) { st->need_rx = 0; return; }   // special case is handled by k_pick
+    if (m == 4 && st->c == 2) return r;   // special case is handled by k_pick
     const bool strategy = (st->mode != 0 && m > st->fallback);
-    tl_stamp(st, TL_SEL0);
+    int cx, cy;
     if (!strategy) {
         double bq = st->scanQ;
         unsigned long long bk = st->scanKey;
         if (effective_world(st->world, m) > 1) {
             const int par = st->iter & 1;
             bq = INFINITY; bk = ~0ull;
-            const long long want = st->run_tag + (long long)st->iter + 1;   // posted by every rank's k_scan of this iteration
+            const long long want = st->run_tag + (long long)st->iter + 1;   // posted by every rank's scan of this iteration
             const unsigned long long t_start = global_ns();
-            for (int r = 0; r < st->world; ++r) {
-                const MailSlot* ms = &mail->slot[par][r];
+            for (int k = 0; k < st->world; ++k) {
+                const MailSlot* ms = &mail->slot[par][k];
                 unsigned spins = 0;
                 while (mail_load_tag(ms) != want) {
-                    if ((++spins & 0x3ff) == 0 && global_ns() - t_start > MAIL_TIMEOUT_NS) {
-                        st->error = 30; st->done = 1; st->skip = 1;   // a peer never posted (failed / diverged): surface FNN_E_STATE
-                        return;
-                    }
+                    if ((++spins & 0x3ff) == 0 && global_ns() - t_start > MAIL_TIMEOUT_NS) { r.ok = 0; return r; }   // a peer never posted
                 }
-                double q; unsigned long long k;
-                mail_load_payload(ms, q, k);
-                if (better(q, k, bq, bk)) { bq = q; bk = k; }
+                double q; unsigned long long key;
+                mail_load_payload(ms, q, key);
+                if (better(q, key, bq, bk)) { bq = q; bk = key; }
             }
         }
         // the cluster the scan had masked, evaluated exactly by k_chain_patch
         if (better(st->patchQ, st->patchKey, bq, bk)) { bq = st->patchQ; bk = st->patchKey; }
-        st->selQ = bq;
-        st->sel_i = (int)(bk >> 32);
-        st->sel_j = (int)(bk & 0xffffffffu);
-    }
-    int cx, cy;
-    if (strategy) { cx = p2s[st->cx_pos]; cy = p2s[st->cy_pos]; }   // Relaxed: k_relaxed_select, Random: k_random_eval
-    else { cx = p2s[st->sel_i]; cy = p2s[st->sel_j]; }
-    if (id[cx] > id[cy]) { int t = cx; cx = cy; cy = t; }
-    st->cx = cx; st->cxn = cx < P2 ? (cx ^ 1) : -1;
-    st->cy = cy; st->cyn = cy < P2 ? (cy ^ 1) : -1;
-    st->need_rx = (st->cxn >= 0 || st->cyn >= 0);
-    if (!strategy) st->alg_bytes += 4.0 * (double)m * ((double)m - 1.0) - 4.0 * (double)P2 + 8.0 * (double)m;
-    tl_stamp(st, TL_SEL1);
-}
-__global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s, DevState* st, Mailbox* mail) {
-    if (st->done || threadIdx.x != 0) return;
-    select_body(id, p2s, st, mail);
+        r.q = bq; r.i = (int)(bk >> 32); r.j = (int)(bk & 0xffffffffu);
+        cx = p2s[r.i]; cy = p2s[r.j];
+    } else { cx = p2s[st->cx_pos]; cy = p2s[st->cy_pos]; }   // Relaxed: k_relaxed_select, Random: k_random_eval
+    if (id[cx] > id[cy]) { const int t = cx; cx = cy; cy = t; }
+    r.cx = cx; r.cxn = cx < P2 ? (cx ^ 1) : -1;
+    r.cy = cy; r.cyn = cy < P2 ? (cy ^ 1) : -1;
+    r.need_rx = (r.cxn >= 0 || r.cyn >= 0);
+    return r;
 }
 
 // ------------------------------------------------------------------ K3b: ComputeRx operands on all SMs
@@ -328,12 +318,30 @@ __global__ void k_select(const int* __restrict__ id, const int* __restrict__ p2s
 //     certified pick of k_pick, which bounds the difference to the reference's left-to-right sum);
 //   * rxs[r][k*1024 + t] = term of position i = t*L + k (segment-transposed, so the exact summation block reads coalesced).
 __global__ void __launch_bounds__(256)
-k_rx_stage(const double* __restrict__ D, int64_t ld, const int* __restrict__ pos, const DevState* st, double* __restrict__ rxs,
-           int64_t rxs_ld, double* __restrict__ rx_part) {
-    if (st->done || !st->need_rx) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) tl_stamp(const_cast<DevState*>(st), TL_RX0);
+k_rx_stage(const double* __restrict__ D, int64_t ld, const int* __restrict__ id, const int* __restrict__ pos,
+           const int* __restrict__ p2s, DevState* st, const Mailbox* mail, double* __restrict__ rxs, int64_t rxs_ld,
+           double* __restrict__ rx_part) {
+    if (st->done) return;
+    __shared__ Sel sel;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) tl_stamp(st, TL_SEL0);
+        sel = select_decode(id, p2s, st, mail);
+        if (blockIdx.x == 0) {   // publish for k_pick
+            if (!sel.ok) { st->error = 30; st->done = 1; st->skip = 1; }   // a peer rank never posted: surface FNN_E_STATE
+            const int m_ = st->m;
+            const bool strategy = (st->mode != 0 && m_ > st->fallback);
+            st->cx = sel.cx; st->cxn = sel.cxn; st->cy = sel.cy; st->cyn = sel.cyn; st->need_rx = sel.need_rx;
+            if (!strategy && sel.cx >= 0) {
+                st->selQ = sel.q; st->sel_i = sel.i; st->sel_j = sel.j;
+                st->alg_bytes += 4.0 * (double)m_ * ((double)m_ - 1.0) - 4.0 * (double)st->P2 + 8.0 * (double)m_;
+            }
+            tl_stamp(st, TL_RX0);
+        }
+    }
+    __syncthreads();
+    if (!sel.ok || !sel.need_rx) return;
     const int m = st->m, P2 = st->P2;
-    const int Cx = st->cx, Cxn = st->cxn, Cy = st->cy, Cyn = st->cyn;
+    const int Cx = sel.cx, Cxn = sel.cxn, Cy = sel.cy, Cyn = sel.cyn;
     const int L = (m + xsum::THREADS - 1) / xsum::THREADS;
     const int zs[4] = {Cx, Cxn, Cy, Cyn};
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -365,7 +373,7 @@ k_rx_stage(const double* __restrict__ D, int64_t ld, const int* __restrict__ pos
         for (int w = 0; w < 8; ++w) v += wsum[w][threadIdx.x];
         rx_part[blockIdx.x * 8 + threadIdx.x] = v;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) tl_stamp(const_cast<DevState*>(st), TL_RX1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) tl_stamp(st, TL_RX1);
 }
 
 // ------------------------------------------------------------------ K3: pick + bookkeeping (one block)
@@ -414,7 +422,7 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
         return;
     }
 
-    const int Cx = st->cx, Cxn = st->cxn, Cy = st->cy, Cyn = st->cyn;   // k_select
+    const int Cx = st->cx, Cxn = st->cxn, Cy = st->cy, Cyn = st->cyn;   // k_rx_stage (select_decode)
 
     // ---- warm this SM's L1 with the O(1) scalars the single control thread is about to chase one after another
     // (the 4x4 distances among the chosen nodes, id/pos of the chosen and of the slots a layout move can touch)
@@ -770,11 +778,10 @@ k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevSta
 // Runs on a forked graph branch, concurrently with the NEXT iteration's selection scan (which reads the new cluster's Sx
 // as -inf).  (1) u.Sx = left-to-right sum of Dpu in position order (NetMakerOriginal.java:530-535), bit-exact;
 // (2) Q of (u-cluster, every other cluster) with that exact u.Sx, in the reference's role order (:215-226), min-loc on the
-// same (Q, i, j) key as the scan; (3) single GPU, canonical: the second of {scan's last block, this block} to arrive merges
-// the two partial min-locs and decodes Cx, Cy.
+// same (Q, i, j) key as the scan.  k_rx_stage (after the graph join) merges the two partial min-locs.
 __global__ void __launch_bounds__(PICK_THREADS, 1)
 k_chain_patch(const double* __restrict__ D, int64_t ld, double* Sx, const int* __restrict__ id, const int* __restrict__ pos,
-              const int* __restrict__ p2s, DevState* st, const double* __restrict__ stage, int serial_chain, int fused_select) {
+              const int* __restrict__ p2s, DevState* st, const double* __restrict__ stage, int serial_chain) {
     extern __shared__ unsigned char smem_raw[];
     double (*buf)[1][CH_TILE] = reinterpret_cast<double (*)[1][CH_TILE]>(smem_raw);
     __shared__ double tot[1];
@@ -800,21 +807,33 @@ k_chain_patch(const double* __restrict__ D, int64_t ld, double* Sx, const int* _
             const int posU = pos[su];
             const double* ru = D + (int64_t)su * ld;
             const double* run = ru + ld;
-            for (int t = tid; t < m; t += PICK_THREADS) {
-                const bool tPair = t < P2;
-                if ((tPair && (t & 1)) || (t & ~1) == su) continue;   // representatives of the other clusters
-                const int pt = pos[t];
-                const double St = Sx[t];
-                const bool uIsP = posU > pt;   // the higher position plays p (:208-213)
-                double dpq;
-                if (tPair) {
-                    const double a = ru[t], b = run[t], c2 = ru[t + 1], d2 = run[t + 1];
-                    dpq = uIsP ? (((a + c2) + b) + d2) * 0.25 : (((a + b) + c2) + d2) * 0.25;
-                } else dpq = (ru[t] + run[t]) * 0.5;
-                const double q = uIsP ? (cm2 * dpq - Su) - St : (cm2 * dpq - St) - Su;
-                const unsigned long long key = uIsP ? (((unsigned long long)posU << 32) | (unsigned)pt)
-                                                    : (((unsigned long long)pt << 32) | (unsigned)posU);
-                if (better(q, key, bq, bk)) { bq = q; bk = key; }
+            constexpr int PU = 4;   // 4 independent element groups per thread: all loads of a sweep are in flight together
+            for (int t0 = tid; t0 < m; t0 += PU * PICK_THREADS) {
+                double a[PU], b[PU], c2[PU], d2[PU], St[PU];
+                int pt[PU];
+                bool use[PU], pr[PU];
+#pragma unroll
+                for (int u = 0; u < PU; ++u) {
+                    const int t = t0 + u * PICK_THREADS;
+                    pr[u] = t < P2;
+                    use[u] = t < m && !(pr[u] && (t & 1)) && (t & ~1) != su;   // representatives of the other clusters
+                    if (use[u]) {
+                        pt[u] = pos[t]; St[u] = Sx[t]; a[u] = ru[t]; b[u] = run[t];
+                        if (pr[u]) { c2[u] = ru[t + 1]; d2[u] = run[t + 1]; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PU; ++u) {
+                    if (!use[u]) continue;
+                    const bool uIsP = posU > pt[u];   // the higher position plays p (:208-213)
+                    double dpq;
+                    if (pr[u]) dpq = uIsP ? (((a[u] + c2[u]) + b[u]) + d2[u]) * 0.25 : (((a[u] + b[u]) + c2[u]) + d2[u]) * 0.25;
+                    else dpq = (a[u] + b[u]) * 0.5;
+                    const double q = uIsP ? (cm2 * dpq - Su) - St[u] : (cm2 * dpq - St[u]) - Su;
+                    const unsigned long long key = uIsP ? (((unsigned long long)posU << 32) | (unsigned)pt[u])
+                                                        : (((unsigned long long)pt[u] << 32) | (unsigned)posU);
+                    if (better(q, key, bq, bk)) { bq = q; bk = key; }
+                }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -833,14 +852,6 @@ k_chain_patch(const double* __restrict__ D, int64_t ld, double* Sx, const int* _
         st->patchQ = bq;
         st->patchKey = bk;
         tl_stamp(st, TL_PATCH1);
-        if (fused_select) {
-            __threadfence();
-            if (atomicAdd(&st->join_ticket, 1u) == 1u) {
-                __threadfence();
-                st->join_ticket = 0;
-                select_body(id, p2s, st, nullptr);
-            }
-        }
     }
 }
 
@@ -891,10 +902,7 @@ struct fnn_ctx {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool join_pending = false;        // a k_chain_patch has been issued on stream2 and not yet waited for
-    // the later of {scan's last block, k_chain_patch} also decodes Cx, Cy (saves the k_select launch) when nothing else
-    // has to be merged or overridden
-    bool fused_select() const { return world == 1 && o.mode == FNN_CANONICAL; }
-    int launches_per_iter() const { return 6 + (fused_select() ? 0 : 1) + (o.mode >= FNN_RANDOM_N ? 2 : 0) + (o.mode == FNN_RELAXED ? 1 : 0); }
+    int launches_per_iter() const { return 6 + (o.mode >= FNN_RANDOM_N ? 2 : 0) + (o.mode == FNN_RELAXED ? 1 : 0); }
     DevState* h_st = nullptr;  // pinned
     CUtensorMap tmap;
     bool have_tmap = false;
@@ -1124,8 +1132,7 @@ extern "C" int fnn_ctx_matrix_ptr(fnn_ctx* c, double** dptr, int64_t* ld) {
 static_assert(PICK_THREADS == xsum::THREADS, "exact-sum block size");
 
 static inline void launch_scan(fnn_ctx* c) {
-    tma::k_scan_tma<<<c->scan_grid, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials, c->peers,
-                                                                              c->id, c->p2s, c->fused_select() ? 1 : 0);
+    tma::k_scan_tma<<<c->scan_grid, tma::THREADS, tma::SMEM_BYTES, c->stream>>>(c->tmap, c->Sx, c->pos, c->st, c->partials, c->peers);
 }
 
 // 2-D tiled tensor map over the n x ld matrix: box = 256 columns x 8 rows, no swizzle, zero OOB fill
@@ -1160,8 +1167,7 @@ static inline void launch_rest(fnn_ctx* c) {
     if (c->o.mode == FNN_RELAXED)
         modes::k_relaxed_select<<<1, modes::THREADS, sizeof(xsum::Smem), c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st,
                                                                                      c->rl_machine, (int)c->n);
-    if (!c->fused_select()) k_select<<<1, 32, 0, c->stream>>>(c->id, c->p2s, c->st, c->mail);
-    k_rx_stage<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->pos, c->st, c->rxs, c->rxs_ld, c->rx_part);
+    k_rx_stage<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->id, c->pos, c->p2s, c->st, c->mail, c->rxs, c->rxs_ld, c->rx_part);
     k_pick<<<1, PICK_THREADS, PICK_SMEM, c->stream>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->amalg, c->trace,
                                                     c->serial_chain, c->rxs, c->rxs_ld, c->rx_part, c->row_grid, c->force_exact);
     k_rows<<<c->row_grid, 256, 0, c->stream>>>(c->D, c->ld, c->Sx, c->st, c->scratch);
@@ -1172,8 +1178,7 @@ static inline void launch_rest(fnn_ctx* c) {
         cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
         cs = c->stream2;
     }
-    k_chain_patch<<<1, PICK_THREADS, CHAIN_SMEM, cs>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->stage, c->serial_chain,
-                                                      c->fused_select() ? 1 : 0);
+    k_chain_patch<<<1, PICK_THREADS, CHAIN_SMEM, cs>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->stage, c->serial_chain);
     if (c->overlap) { cudaEventRecord(c->ev_join, c->stream2); c->join_pending = true; }
 }
 // the forked branch has to be back on the main stream before a capture ends, before the state is read, before the next run
@@ -1332,7 +1337,8 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
     if (c->tl) {   // dump the timeline window (ns since its first stamp)
         std::vector<unsigned long long> h((size_t)TL_EVENTS * c->tl_count);
         FNN_CUDA(cudaMemcpy(h.data(), c->tl, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        if (FILE* f = fopen(c->tl_path.c_str(), "w")) {
+        const std::string path = c->world > 1 ? c->tl_path + ".r" + std::to_string(c->rank) : c->tl_path;
+        if (FILE* f = fopen(path.c_str(), "w")) {
             fprintf(f, "iter,scan0,scan1,rx0,rx1,pick0,pick1,rows0,rows1,scat0,scat1,chain0,chain1,patch1,sel0,sel1\n");
             unsigned long long base = 0;
             for (size_t i = 0; i < h.size() && !base; ++i) base = h[i];

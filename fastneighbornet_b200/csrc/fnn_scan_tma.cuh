@@ -196,8 +196,7 @@ __device__ __forceinline__ void eval_pp(const double* sm, const RowData* rd, dou
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ Sx, const int* __restrict__ pos,
-           DevState* st, Partial* partials, const PeerTable* peers, const int* __restrict__ ids, const int* __restrict__ p2s,
-           int fused_select) {
+           DevState* st, Partial* partials, const PeerTable* peers) {
     if (st->done || (st->mode != 0 && st->m > st->fallback)) return;   // NetMakerOriginal.java:361-366
     extern __shared__ __align__(1024) unsigned char smem[];
     // keep the ring pointer in the shared window (no generic-address loads): offset, not integer cast
@@ -389,28 +388,17 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
             st->ticket = 0;
             tl_stamp(st, TL_SCAN1);
             if (ew > 1) {
-                // post this rank's partial into every rank's mailbox (own included); k_select merges
+                // post this rank's partial into every rank's mailbox (own included); every block of k_rx_stage merges.
+                // Payloads first, ONE system-scope fence, then the tags.
                 const int par = st->iter & 1;
                 const long long tag = st->run_tag + (long long)st->iter + 1;
-                for (int r = 0; r < st->world; ++r) {
-                    MailSlot* ms = &peers->box[r]->slot[par][st->rank];
-                    mail_store_payload(ms, bq, bk);
-                }
-                __threadfence_system();   // payload before tag, system scope
+                for (int r = 0; r < st->world; ++r) mail_store_payload(&peers->box[r]->slot[par][st->rank], bq, bk);
+                __threadfence_system();
                 for (int r = 0; r < st->world; ++r) mail_store_tag(&peers->box[r]->slot[par][st->rank], tag);
             } else {
+                // merged with k_chain_patch's partial (the masked cluster) and decoded by k_rx_stage
                 st->scanQ = bq;
                 st->scanKey = bk;
-                // single GPU, canonical: whichever of {this block, k_chain_patch} arrives second merges the two partial
-                // min-locs and decodes Cx, Cy (saves the k_select launch); otherwise k_select does it after the join
-                if (fused_select) {
-                    __threadfence();
-                    if (atomicAdd(&st->join_ticket, 1u) == 1u) {
-                        __threadfence();
-                        st->join_ticket = 0;
-                        select_body(ids, p2s, st, nullptr);
-                    }
-                }
             }
         }
     }

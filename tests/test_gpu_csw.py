@@ -49,6 +49,53 @@ def test_split_weights_bit_exact_vs_l1(fnn, n, seed, eps):
     assert np.abs(x - x0).max() < 2e-3
 
 
+@pytest.mark.parametrize("n", [4, 5, 6, 9, 33, 64, 120, 257])
+def test_literal_matvecs_bit_exact_vs_literal_oracle(fnn, n):
+    """The literal-order device path (namespace lit in csrc/fnn_csw.cu: the reference's n-1 dependent diagonals, rowsum in
+    index order) against the literal CPU restatement of CircularSplitWeights.java:571-731 - bit for bit."""
+    rng = np.random.default_rng(100 + n)
+    for v in (rng.random(n * (n - 1) // 2), rng.normal(0, 1, n * (n - 1) // 2)):
+        assert (fnn.csw_matvec("ab", v, n, variant="literal") == oracle.ab(n, v)).all()
+        assert (fnn.csw_matvec("atx", v, n, variant="literal") == oracle.atx(n, v)).all()
+
+
+@pytest.mark.parametrize("n,seed,eps", [(8, 1, 0.05), (20, 1, 0.05), (40, 2, 0.05), (60, 3, 0.2), (80, 1, 0.05), (120, 4, 0.05)])
+def test_split_weights_literal_order_bit_exact_vs_literal_oracle(fnn, n, seed, eps):
+    """a CUDA path against the LITERAL oracle (L0), not against a restatement of the GPU's own
+    formulation.  Every sum in the reference's order (left-to-right norm and alpha dot through the exact summation,
+    wavefront mat-vecs) => identical active-set path, identical CG iteration counts, identical weights."""
+    D, o, du = _problem(n, seed, eps)
+    x, st = fnn.split_weights(o, du, variant="literal")
+    d_pos = oracle.setup_d(o, du)
+    x0, s0 = oracle.split_weights(n, d_pos)
+    assert (st["cg_iters"], st["cg_calls"], st["outer"], st["inner"]) == (s0["cg_iters"], s0["cg_calls"], s0["outer"], s0["inner"])
+    assert (x == x0).all(), np.abs(x - x0).max()
+    assert np.abs(x - x0).max() <= 1e-9 * max(1.0, np.abs(x0).max())   # the north star's bound, met with zero difference
+
+
+@pytest.mark.parametrize("n,seed,eps", [(40, 2, 0.05), (80, 1, 0.05), (120, 4, 0.05), (200, 7, 0.05)])
+def test_production_formulation_vs_literal_order(fnn, n, seed, eps):
+    """What the production formulation (2-D prefix sums, fixed trees) costs against the reference's order: the split SET
+    (x > 1e-6, FastNN.java:455-466) and the kept weights.  The active-set algorithm stops at a 1e-8 relative residual and a
+    -1e-7 gradient, so two summation orders land on slightly different feasible points: the split sets agree up to
+    splits whose weight is at the noise floor, and the weights that matter agree to ~1e-5 relative."""
+    D, o, du = _problem(n, seed, eps)
+    xf, _ = fnn.split_weights(o, du)
+    xl, _ = fnn.split_weights(o, du, variant="literal")
+    kf, kl = xf > 1e-6, xl > 1e-6
+    sym = np.nonzero(kf != kl)[0]
+    both = kf & kl
+    rel = np.abs(xf[both] - xl[both]) / xl[both]
+    big = both & (xl > 1e-3 * xl.max())
+    rel_big = np.abs(xf[big] - xl[big]) / xl[big]
+    print(f"n={n}: kept {int(kf.sum())} / {int(kl.sum())}, symmetric difference {sym.size}, "
+          f"max rel diff over kept {rel.max():.2e}, over weights > 1e-3*max {rel_big.max():.2e}, max abs {np.abs(xf - xl).max():.2e}")
+    assert np.abs(xf - xl).max() < 2e-3
+    assert sym.size <= max(2, int(0.02 * kl.sum()))
+    assert np.maximum(xf[sym], xl[sym]).max(initial=0.0) < 1e-3   # a split in only one set carries a noise-level weight
+    assert rel_big.max() < 1e-2
+
+
 def test_additive_tree_needs_no_iterations(fnn):
     """eps = 0: the unconstrained optimum is feasible up to rounding; weights reproduce the tree."""
     D, o, du = _problem(30, 5, 0.0)

@@ -10,8 +10,8 @@ nxt_scan0 = np.roll(c["scan0"], -1); nxt_scan0[-1] = np.nan
 prev_scat1 = np.roll(c["scat1"], 1); prev_scat1[0] = np.nan
 rows = {
     "scan": c["scan1"] - c["scan0"],
-    "sel(after scan1)": c["sel1"] - c["scan1"],
-    "sel1->rx0": c["rx0"] - c["sel1"],
+    "scan1->sel0 (boundary)": c["sel0"] - c["scan1"],
+    "select decode (in k_rx_stage)": c["rx0"] - c["sel0"],
     "rx": c["rx1"] - c["rx0"],
     "rx1->pick0": c["pick0"] - c["rx1"],
     "pick": c["pick1"] - c["pick0"],
