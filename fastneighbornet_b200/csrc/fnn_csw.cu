@@ -122,18 +122,25 @@ __global__ void k_colscan_fix(double* __restrict__ P, const double* __restrict__
     }
 }
 
-// PRS[a] = sum_{a' <= a} (RT[a'] + CT[a']), strictly left to right; operands staged through shared memory in parallel
-__global__ void __launch_bounds__(1024) k_prs(const double* RT, const double* CT, double* PRS, int n, const int* done) {
-    if (done && *done) return;
-    extern __shared__ double stage[];
-    for (int a = threadIdx.x; a < n; a += blockDim.x) stage[a] = RT[a] + CT[a];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double acc = 0.0;
-        for (int a = 0; a < n; ++a) { acc = acc + stage[a]; stage[a] = acc; }
+// PRS[a] = prefix over a' <= a of (RT[a'] + CT[a']): blocks of 32 scanned Kogge-Stone, carry added sequentially (the order of
+// the row pass; a single dependent chain of n adds cost ~13 us at n = 800).  One warp.
+__device__ __forceinline__ void prs_scan_warp(const double* RT, const double* CT, double* PRS, int n, int lane) {
+    double carry = 0.0;
+    for (int blk = 0; blk < n; blk += 32) {
+        double e = (blk + lane < n) ? RT[blk + lane] + CT[blk + lane] : 0.0;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, e, off);
+            if (lane >= off) e = e + t;
+        }
+        const double out = carry + e;
+        if (blk + lane < n) PRS[blk + lane] = out;
+        carry = __shfl_sync(0xffffffffu, out, 31);
     }
-    __syncthreads();
-    for (int a = threadIdx.x; a < n; a += blockDim.x) PRS[a] = stage[a];
+}
+__global__ void __launch_bounds__(32) k_prs(const double* RT, const double* CT, double* PRS, int n, const int* done) {
+    if (done && *done) return;
+    prs_scan_warp(RT, CT, PRS, n, threadIdx.x);
 }
 
 // ---------------------------------------------------------------- fixed reduction tree (level 1 inside producers)
@@ -387,6 +394,456 @@ __global__ void k_setup_d(const double* __restrict__ d_upper, const int* __restr
 }
 
 
+// ============================================================================ persistent CG loop (one launch per CG solve)
+// The loop body of circularConjugateGrads (:797-829) is ~20 dependent launches in the graph path (~45-85 us per iteration
+// regardless of n, 10^4-10^6 iterations per solve).  k_cg_persistent runs the WHOLE loop in one cooperative launch: the
+// phases of an iteration are separated by grid barriers (one atomic + one acquire spin per CTA) instead of kernel
+// boundaries.  Every scan, combine and reduction keeps the operand order of the per-phase kernels above, so the L1 oracle
+// is the bit-exact check for both paths:
+//   * the p update is fused into the row scan of A p; k_ab_combine is fused into the row scan of A^T y;
+//   * k_colscan_fix is folded into its consumers: P stays chunk-local and every read adds its carry, `carry[j] + P[q]`,
+//     exactly the operands and order of the in-place fix;
+//   * PRS (one warp) and the upper levels of the two reduction trees are recomputed redundantly by every CTA, so alpha,
+//     rho and the loop test need no broadcast and every CTA takes the same control decisions.
+// 8 grid barriers per iteration.  Buffers written inside the kernel carry no const/__restrict__ (no ld.global.nc).
+struct CgArgs {
+    double *x, *r, *p, *w, *y, *Rw, *P, *RT, *CT, *T, *T2, *part1, *part2;
+    const unsigned char* active;
+    Scalars* sc;
+    unsigned long long* bar;   // [0] arrivals (monotonic), [1] released generation
+    int n, nchunks;
+    long long np, nblk;
+    long long max_iters;       // leave the kernel after this many iterations (0: run to the end): keeps single launches short
+    unsigned long long* prof;  // optional (env FNN_CSW_PROF): ns per phase / barrier accumulated by CTA 0, [24]
+};
+constexpr int CGP_THREADS = 512;          // 128 registers per thread: the phases keep 16-24 independent loads in flight per thread
+constexpr int CGP_Q = CGP_THREADS / 256;    // 256-thread groups, each owns one 1024-entry block of the reduction tree
+constexpr int CGP_MAX_N = 12000;            // two n-vectors of doubles in shared memory (PRS / diagonal, row ends)
+
+// Cross-CTA data is read with ld.global.cg (L2, never this SM's L1): coherent across the grid barriers without relying on
+// L1 invalidation, and - being explicit loads from buffers the compiler cannot prove read-only - free to be hoisted above
+// the stores of the same phase, which go to other buffers.  That hoisting is the point: every phase is a few ROUNDS of
+// independent loads (~0.7 us L2 latency each), not a chain of dependent ones.
+__device__ __forceinline__ double ldg_cg(const double* p) { return __ldcg(p); }
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long nblocks, unsigned long long& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gen += 1;
+        __threadfence();
+        const unsigned long long prev = atomicAdd(&bar[0], 1ull);
+        if (prev + 1 == nblocks * gen) {
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&bar[1]), "l"(gen) : "memory");
+        } else {
+            unsigned long long g;
+            do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(&bar[1]) : "memory"); } while (g < gen);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// k_colscan_fix folded into the consumers: carry[j] + P[q]
+__device__ __forceinline__ double fixed_P(const double* P, const double* T, int n, int i, int j) {
+    return ldg_cg(T + (int64_t)(i / COL_CHUNK) * n + j) + ldg_cg(P + pidx(n, i, j));
+}
+
+// k_tree_level on one block of 1024 values read through `get`, by 256-thread group g of the CTA; result in the group's
+// thread 0.  All threads call (two __syncthreads inside).
+template <typename Get>
+__device__ __forceinline__ double group_tree(Get get, long long base, long long len, int g, int t4, double (*sh8)[8]) {
+    double e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e[q] = (base + 4 * t4 + q < len) ? get(base + 4 * t4 + q) : 0.0;
+    double s = ((e[0] + e[1]) + e[2]) + e[3];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) sh8[g][(threadIdx.x >> 5) & 7] = s;
+    __syncthreads();
+    double t = 0.0;
+    if (t4 == 0) {
+        t = sh8[g][0];
+        for (int w = 1; w < 8; ++w) t = t + sh8[g][w];
+    }
+    __syncthreads();
+    return t;
+}
+
+// levels >= 2 of the fixed tree over part[0..nblk) (finish_tree), recomputed by every CTA; result to all threads.
+// nblk <= 2^20: level 2 leaves at most 1024 values (in lv, shared), level 3 is the root.
+__device__ double cgp_reduce(const double* part, long long nblk, double* lv, double (*sh8)[8], double* bval) {
+    const int g = threadIdx.x >> 8, t4 = threadIdx.x & 255;
+    const long long blocks2 = (nblk + 1023) / 1024;
+    if (blocks2 == 1) {
+        const double t = group_tree([&](long long k) { return ldg_cg(part + k); }, 0, g == 0 ? nblk : 0, g, t4, sh8);
+        if (threadIdx.x == 0) *bval = t;
+    } else {
+        for (long long b0 = 0; b0 < blocks2; b0 += CGP_Q) {
+            const long long vb = b0 + g;
+            const double t = group_tree([&](long long k) { return ldg_cg(part + k); }, vb * 1024, vb < blocks2 ? nblk : 0, g, t4, sh8);
+            if (t4 == 0 && vb < blocks2) lv[vb] = t;
+        }
+        __syncthreads();
+        const double t = group_tree([&](long long k) { return lv[k]; }, 0, g == 0 ? blocks2 : 0, g, t4, sh8);
+        if (threadIdx.x == 0) *bval = t;
+    }
+    __syncthreads();
+    const double v = *bval;
+    __syncthreads();
+    return v;
+}
+
+// blocks of 32 of one row: Kogge-Stone inside, carry added sequentially (k_rowscan); e is this lane's element
+__device__ __forceinline__ double scan32_carry(double e, double& carry, int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, e, off);
+        if (lane >= off) e = e + t;
+    }
+    const double out = carry + e;
+    carry = __shfl_sync(0xffffffffu, out, 31);
+    return out;
+}
+
+// chunk-local column scan of COL_CHUNK rows from zero (k_colscan_local): all loads of a half-chunk first, then the chain
+template <bool WITH_CT>
+__device__ __forceinline__ void colscan_local_thread(const double* Rw, const double* v, double* P, double* T, double* T2, int n, int c,
+                                                     int j) {
+    const int i0 = c * COL_CHUNK, i1 = min(i0 + COL_CHUNK, j);
+    double acc = 0.0, acc2 = 0.0;
+    int64_t q = (i0 < i1) ? pidx(n, i0, j) : 0;
+    constexpr int B = WITH_CT ? 8 : 16;
+    for (int h0 = i0; h0 < i1; h0 += B) {
+        double rw[B], vv[WITH_CT ? B : 1];
+        int64_t qq = q;
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int i = h0 + k;
+            if (i < i1) {
+                rw[k] = ldg_cg(Rw + qq);
+                if (WITH_CT) vv[k] = ldg_cg(v + qq);
+                qq += n - i - 2;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int i = h0 + k;
+            if (i < i1) {
+                acc = acc + rw[k];
+                P[q] = acc;
+                if (WITH_CT) acc2 = acc2 + vv[k];
+                q += n - i - 2;
+            }
+        }
+    }
+    T[(int64_t)c * n + j] = acc;
+    if (WITH_CT) T2[(int64_t)c * n + j] = acc2;
+}
+
+// exclusive carries of the chunk totals of column j (k_colscan_carry), loads batched by 16
+template <bool WITH_CT>
+__device__ __forceinline__ void colscan_carry_thread(double* T, const double* T2, double* CT, int n, int nchunks, int j) {
+    double carry = 0.0, acc2 = 0.0;
+    constexpr int B = WITH_CT ? 8 : 16;
+    for (int c0 = 0; c0 < nchunks; c0 += B) {
+        double t[B], t2[WITH_CT ? B : 1];
+#pragma unroll
+        for (int k = 0; k < B; ++k)
+            if (c0 + k < nchunks) {
+                t[k] = ldg_cg(T + (int64_t)(c0 + k) * n + j);
+                if (WITH_CT) t2[k] = ldg_cg(T2 + (int64_t)(c0 + k) * n + j);
+            }
+#pragma unroll
+        for (int k = 0; k < B; ++k)
+            if (c0 + k < nchunks) {
+                T[(int64_t)(c0 + k) * n + j] = carry;
+                carry = carry + t[k];
+                if (WITH_CT) acc2 = acc2 + t2[k];
+            }
+    }
+    if (WITH_CT) CT[j] = acc2;
+}
+
+template <bool PROF>
+__global__ void __launch_bounds__(CGP_THREADS, 1) k_cg_persistent(CgArgs a) {
+    extern __shared__ double dyn[];          // [0, n): PRS or the diagonal vector; [n, 2n): the row-end vector
+    __shared__ double sh8[CGP_Q][8];
+    __shared__ double lv[1024];
+    __shared__ double bval;
+    const int n = a.n, nchunks = a.nchunks;
+    double* vecA = dyn;
+    double* vecB = dyn + n;
+    const long long np = a.np, nblk = a.nblk;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int gwarp = blockIdx.x * (CGP_THREADS / 32) + (tid >> 5), nwarps = gridDim.x * (CGP_THREADS / 32);
+    const long long gtid = (long long)blockIdx.x * CGP_THREADS + tid, gthreads = (long long)gridDim.x * CGP_THREADS;
+    const int g = tid >> 8, t4 = tid & 255;
+    const unsigned long long nblocks = gridDim.x;
+    unsigned long long gen = 0;
+    if (tid == 0) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(gen) : "l"(&a.bar[1]) : "memory");   // resumed launches continue the count
+
+    // loop-carried scalars, identical in every thread of every CTA
+    double rho = a.sc->rho, rho_old = a.sc->rho_old, beta = a.sc->beta, alpha = a.sc->alpha, dot = a.sc->dot;
+    const double e0sq = a.sc->e0sq;
+    long long k = a.sc->k, iters_total = a.sc->iters_total;
+    const long long kmax = a.sc->kmax;
+    int done = a.sc->done;
+    long long left = a.max_iters;
+    constexpr int U = 8;   // 32-element blocks of a row in flight per warp
+    unsigned long long tacc[PROF ? 20 : 1], tlast = 0;
+    const bool prof = PROF && (a.prof != nullptr) && gtid == 0;
+    if (PROF && prof) {
+#pragma unroll
+        for (int q = 0; q < 20; ++q) tacc[PROF ? q : 0] = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast));
+    }
+#define CG_MARK(slot)                                                        \
+    if (PROF && prof) {                                                      \
+        unsigned long long tn_;                                              \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn_));              \
+        tacc[PROF ? slot : 0] += tn_ - tlast;                                \
+        tlast = tn_;                                                         \
+    }
+
+    while (!done) {
+        // ---- phase 1: p = (k == 1) ? r : r + beta p   (k_pupdate), row scan of p -> Rw   (k_rowscan, no RT)
+        const bool first = (k == 1);
+        for (int i = gwarp; i < n - 1; i += nwarps) {
+            const int64_t rs = row_start(n, i);
+            const int len = n - 1 - i;
+            double carry = 0.0;
+            for (int b0 = 0; b0 < len; b0 += 32 * U) {
+                double rv[U], pv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = b0 + 32 * u + lane;
+                    rv[u] = 0.0; pv[u] = 0.0;
+                    if (idx < len) { rv[u] = ldg_cg(a.r + rs + idx); if (!first) pv[u] = ldg_cg(a.p + rs + idx); }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (b0 + 32 * u < len) {
+                        const int idx = b0 + 32 * u + lane;
+                        double e = 0.0;
+                        if (idx < len) {
+                            e = first ? rv[u] : rv[u] + beta * pv[u];
+                            a.p[rs + idx] = e;
+                        }
+                        const double out = scan32_carry(e, carry, lane);
+                        if (idx < len) a.Rw[rs + idx] = out;
+                    }
+                }
+            }
+        }
+        CG_MARK(0)
+        grid_barrier(a.bar, nblocks, gen);
+        CG_MARK(1)
+        // ---- phase 2: k_colscan_local<false>
+        for (long long idx = gtid; idx < (long long)nchunks * n; idx += gthreads)
+            colscan_local_thread<false>(a.Rw, nullptr, a.P, a.T, a.T2, n, (int)(idx / n), (int)(idx % n));
+        CG_MARK(2)
+        grid_barrier(a.bar, nblocks, gen);
+        CG_MARK(3)
+        // ---- phase 3: k_colscan_carry<false>
+        for (long long j = gtid; j < n; j += gthreads) colscan_carry_thread<false>(a.T, nullptr, nullptr, n, nchunks, (int)j);
+        CG_MARK(4)
+        grid_barrier(a.bar, nblocks, gen);
+        CG_MARK(5)
+        // ---- phase 4: y = A p from P (k_ab_combine, with the fix folded in), row scan of y -> Rw, RT   (k_rowscan)
+        // the two n-vectors every entry needs, once per CTA: vecA[b] = P(b-1,b-1) = fixed P at (b-2, b-1), vecB[b] = P(b-1,n-1)
+        for (int b = tid; b < n; b += CGP_THREADS) {
+            vecA[b] = (b - 1 >= 1) ? fixed_P(a.P, a.T, n, b - 2, b - 1) : 0.0;
+            vecB[b] = (b >= 1) ? fixed_P(a.P, a.T, n, b - 1, n - 1) : 0.0;
+        }
+        __syncthreads();
+        for (int i = gwarp; i < n - 1; i += nwarps) {
+            const int64_t rs = row_start(n, i);
+            const int len = n - 1 - i;
+            const double Pda = vecA[i];
+            const double Prowa = vecB[i];
+            const double* Trow = a.T + (int64_t)((i >= 1 ? i - 1 : 0) / COL_CHUNK) * n;
+            const int64_t prow = (i >= 1) ? pidx(n, i - 1, 0) : 0;   // P(i-1, b-1) sits at prow + (b-1)
+            double carry = 0.0;
+            for (int b0 = 0; b0 < len; b0 += 32 * U) {
+                double tc[U], pl[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = b0 + 32 * u + lane;
+                    tc[u] = 0.0; pl[u] = 0.0;
+                    if (idx < len && i >= 1) {
+                        const int b = i + 1 + idx;
+                        tc[u] = ldg_cg(Trow + (b - 1));
+                        pl[u] = ldg_cg(a.P + prow + (b - 1));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (b0 + 32 * u < len) {
+                        const int idx = b0 + 32 * u + lane;
+                        double e = 0.0;
+                        if (idx < len) {
+                            const int b = i + 1 + idx;
+                            const double P1 = (i >= 1) ? tc[u] + pl[u] : 0.0;
+                            double t = 2.0 * P1;
+                            t = t - Pda;
+                            t = t + vecB[b];
+                            t = t - Prowa;
+                            t = t - vecA[b];
+                            e = t;
+                            a.y[rs + idx] = t;
+                        }
+                        const double out = scan32_carry(e, carry, lane);
+                        if (idx < len) a.Rw[rs + idx] = out;
+                    }
+                }
+            }
+            if (lane == 0) a.RT[i] = carry;
+        }
+        if (gtid == 0) a.RT[n - 1] = 0.0;
+        CG_MARK(6)
+        grid_barrier(a.bar, nblocks, gen);   // phase 4 reads P/T of the first prefix and writes Rw/y/RT only; P/T are rewritten after this barrier
+        CG_MARK(7)
+        // ---- phase 5: k_colscan_local<true>
+        for (long long idx = gtid; idx < (long long)nchunks * n; idx += gthreads)
+            colscan_local_thread<true>(a.Rw, a.y, a.P, a.T, a.T2, n, (int)(idx / n), (int)(idx % n));
+        CG_MARK(8)
+        grid_barrier(a.bar, nblocks, gen);
+        CG_MARK(9)
+        // ---- phase 6: k_colscan_carry<true>
+        for (long long j = gtid; j < n; j += gthreads) colscan_carry_thread<true>(a.T, a.T2, a.CT, n, nchunks, (int)j);
+        CG_MARK(10)
+        grid_barrier(a.bar, nblocks, gen);
+        CG_MARK(11)
+        // ---- phase 7 (per CTA): k_prs -> vecA; vecB[j] = G(j,j) = fixed G at (j-1, j)
+        if (tid < 32) {
+            double carry = 0.0;
+            for (int blk = 0; blk < n; blk += 32) {
+                const double e = (blk + lane < n) ? ldg_cg(a.RT + blk + lane) + ldg_cg(a.CT + blk + lane) : 0.0;
+                const double out = scan32_carry(e, carry, lane);
+                if (blk + lane < n) vecA[blk + lane] = out;
+            }
+        }
+        for (int j = tid; j < n; j += CGP_THREADS) vecB[j] = (j >= 1) ? fixed_P(a.P, a.T, n, j - 1, j) : 0.0;
+        __syncthreads();
+        CG_MARK(12)
+        // ---- phase 8: w = mask(A^T y), partial products p.w   (k_atx_combine<1>, fix folded in)
+        for (long long vb0 = (long long)blockIdx.x * CGP_Q; vb0 < nblk; vb0 += (long long)gridDim.x * CGP_Q) {
+            const long long vb = vb0 + g;
+            const bool valid = vb < nblk;
+            const int64_t base = (int64_t)vb * 1024 + 4 * t4;
+            double prod[4] = {0.0, 0.0, 0.0, 0.0};
+            if (valid && base < np) {
+                int64_t i = (int64_t)(((2.0 * n - 1.0) - sqrt((2.0 * n - 1.0) * (2.0 * n - 1.0) - 8.0 * (double)base)) * 0.5);
+                while (i > 0 && row_start(n, i) > base) --i;
+                while (row_start(n, i + 1) <= base) ++i;
+                int64_t j = base - row_start(n, i) + i + 1;
+                double tc[4], pl[4], pp[4];
+                int ii[4], jj[4];
+                bool act[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int64_t kk = base + q;
+                    ii[q] = (int)i; jj[q] = (int)j;
+                    if (kk < np) {
+                        tc[q] = ldg_cg(a.T + (int64_t)((int)i / COL_CHUNK) * n + j);
+                        pl[q] = ldg_cg(a.P + kk);
+                        pp[q] = ldg_cg(a.p + kk);
+                        act[q] = a.active[kk] != 0;
+                        if (++j == n) { ++i; j = i + 1; }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int64_t kk = base + q;
+                    if (kk < np) {
+                        const double u = vecA[jj[q]] - vecA[ii[q]];
+                        const double Gij = tc[q] + pl[q];
+                        const double wv = vecB[jj[q]] - Gij;
+                        double pv = u - 2.0 * wv;
+                        if (act[q]) pv = 0.0;
+                        prod[q] = pp[q] * pv;
+                        a.w[kk] = pv;
+                    }
+                }
+            }
+            double s = ((prod[0] + prod[1]) + prod[2]) + prod[3];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+            if ((tid & 31) == 0) sh8[g][(tid >> 5) & 7] = s;
+            __syncthreads();
+            if (t4 == 0 && valid) {
+                double t = sh8[g][0];
+                for (int w = 1; w < 8; ++w) t = t + sh8[g][w];
+                a.part1[vb] = t;
+            }
+            __syncthreads();
+        }
+        CG_MARK(13)
+        grid_barrier(a.bar, nblocks, gen);
+        CG_MARK(14)
+        // ---- phase 9: EP_ALPHA
+        dot = cgp_reduce(a.part1, nblk, lv, sh8, &bval);
+        alpha = rho / dot;
+        CG_MARK(15)
+        // ---- phase 10: x += alpha p ; r -= alpha w ; partials r.r   (k_xr_update)
+        for (long long vb0 = (long long)blockIdx.x * CGP_Q; vb0 < nblk; vb0 += (long long)gridDim.x * CGP_Q) {
+            const long long vb = vb0 + g;
+            const bool valid = vb < nblk;
+            const int64_t base = (int64_t)vb * 1024 + 4 * t4;
+            double e[4] = {0.0, 0.0, 0.0, 0.0};
+            if (valid) {
+                double xv[4], pv[4], rv[4], wv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (base + q < np) {
+                        xv[q] = ldg_cg(a.x + base + q); pv[q] = ldg_cg(a.p + base + q);
+                        rv[q] = ldg_cg(a.r + base + q); wv[q] = ldg_cg(a.w + base + q);
+                    }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (base + q < np) {
+                        a.x[base + q] = xv[q] + alpha * pv[q];
+                        const double nr = rv[q] - alpha * wv[q];
+                        a.r[base + q] = nr;
+                        e[q] = nr * nr;
+                    }
+            }
+            double s = ((e[0] + e[1]) + e[2]) + e[3];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+            if ((tid & 31) == 0) sh8[g][(tid >> 5) & 7] = s;
+            __syncthreads();
+            if (t4 == 0 && valid) {
+                double t = sh8[g][0];
+                for (int w = 1; w < 8; ++w) t = t + sh8[g][w];
+                a.part2[vb] = t;
+            }
+            __syncthreads();
+        }
+        CG_MARK(16)
+        grid_barrier(a.bar, nblocks, gen);
+        CG_MARK(17)
+        // ---- phase 11: EP_RHO_STEP and the loop test (:796)
+        const double val = cgp_reduce(a.part2, nblk, lv, sh8, &bval);
+        rho_old = rho;
+        iters_total += 1;
+        rho = val;
+        if ((val > e0sq) && (k < kmax)) { k += 1; if (k > 1) beta = val / rho_old; }
+        else done = 1;
+        CG_MARK(18)
+        if (!done && a.max_iters > 0 && --left == 0) break;   // same decision in every CTA: resumable
+    }
+    if (gtid == 0) {
+        a.sc->rho = rho; a.sc->rho_old = rho_old; a.sc->beta = beta; a.sc->alpha = alpha; a.sc->dot = dot;
+        a.sc->k = k; a.sc->iters_total = iters_total; a.sc->done = done;
+    }
+    if (PROF && prof) {
+#pragma unroll
+        for (int q = 0; q < 20; ++q) a.prof[q] += tacc[PROF ? q : 0];
+    }
+#undef CG_MARK
+}
+
 // ============================================================================ literal-order path (parity ladder L0 on the device)
 // opts.reserved[4] = 2.  The SAME arithmetic as CircularSplitWeights.java in the SAME order, so that the weights can be held
 // bit for bit against the literal CPU restatement (oracle/nnet_oracle.cpp) - the check the production formulation above
@@ -526,6 +983,10 @@ struct Csw {
     Scalars* h_sc = nullptr;
     cudaGraphExec_t cg_graph = nullptr;
     int64_t cg_calls = 0, outer = 0, inner = 0, launches = 0, launches_per_graph = 0;
+    int persistent = 0;        // 1: k_cg_persistent (one cooperative launch per CG solve) instead of the graph path
+    int persistent_grid = 0;
+    unsigned long long* bar = nullptr;
+    unsigned long long* prof = nullptr;   // FNN_CSW_PROF: per-phase ns of k_cg_persistent (CTA 0)
     int literal = 0;           // opts.reserved[4] == 2: the reference's own operation order (namespace lit), n <= 512
     // cub scratch and the 60 % collapse work arrays
     void* tmp = nullptr;
@@ -547,8 +1008,9 @@ struct Csw {
         CSW_ALLOC(RT, n); CSW_ALLOC(CT, n); CSW_ALLOC(PRS, n);
         nchunks = (n + COL_CHUNK - 1) / COL_CHUNK;
         CSW_ALLOC(T, (size_t)nchunks * n); CSW_ALLOC(T2, (size_t)nchunks * n);
-        FNN_CUDA(cudaFuncSetAttribute(k_prs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * n)));
-        CSW_ALLOC(part1, nblk + 1); CSW_ALLOC(part2, (nblk + 1023) / 1024 + 1);
+        CSW_ALLOC(part1, nblk + 1); CSW_ALLOC(part2, nblk + 1);   // part2: level-2 scratch, or the r.r partials of k_cg_persistent
+        CSW_ALLOC(bar, 2);
+        if (getenv("FNN_CSW_PROF")) { CSW_ALLOC(prof, 24); FNN_CUDA(cudaMemset(prof, 0, 24 * sizeof(unsigned long long))); }
         CSW_ALLOC(active, np); CSW_ALLOC(sc, 1);
         CSW_ALLOC(neg, np); CSW_ALLOC(neg_sorted, np); CSW_ALLOC(tie_flag, np); CSW_ALLOC(tie_rank, np); CSW_ALLOC(d_count, 1);
         FNN_CUDA(cudaMalloc(&d_minloc, 16));
@@ -561,7 +1023,7 @@ struct Csw {
         if (cg_graph) cudaGraphExecDestroy(cg_graph);
         cudaFree(d); cudaFree(x); cudaFree(r); cudaFree(w); cudaFree(p); cudaFree(y); cudaFree(old_x); cudaFree(AtWd);
         cudaFree(T); cudaFree(T2); cudaFree(Rw); cudaFree(P); cudaFree(RT); cudaFree(CT); cudaFree(PRS); cudaFree(part1); cudaFree(part2);
-        cudaFree(active); cudaFree(sc);
+        cudaFree(active); cudaFree(sc); cudaFree(bar); cudaFree(prof);
         cudaFree(neg); cudaFree(neg_sorted); cudaFree(tie_flag); cudaFree(tie_rank); cudaFree(d_count); cudaFree(d_minloc); cudaFree(tmp);
         if (h_sc) cudaFreeHost(h_sc);
         if (st) cudaStreamDestroy(st);
@@ -588,7 +1050,7 @@ struct Csw {
     void Atx_prefix(const double* in, const int* gate) {
         k_rowscan<<<std::min(n, 148 * 8), 256, 0, st>>>(in, Rw, RT, n, gate);
         colscan<true>(in, gate);
-        k_prs<<<1, 1024, sizeof(double) * n, st>>>(RT, CT, PRS, n, gate);
+        k_prs<<<1, 32, 0, st>>>(RT, CT, PRS, n, gate);
         launches += 5;
     }
     void Atx(const double* in, double* out, const int* gate) {
@@ -638,6 +1100,22 @@ struct Csw {
         k_residual_init<<<(unsigned)nblk, 256, 0, st>>>(r, AtWd, active, np, part1);
         finish_tree(EP_RHO_INIT, 0);
         launches += 1;
+        if (persistent) {
+            // bounded launches (the kernel is resumable: all loop state lives in Scalars and the barrier words)
+            const long long per_launch = 1 << 16;
+            FNN_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned long long), st));
+            while (true) {
+                FNN_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+                FNN_CUDA(cudaStreamSynchronize(st));
+                if (h_sc->done) break;
+                CgArgs a{x, r, p, w, y, Rw, P, RT, CT, T, T2, part1, part2, active, sc, bar, n, nchunks, (long long)np, (long long)nblk, per_launch, prof};
+                void* params[] = {&a};
+                FNN_CUDA(cudaLaunchCooperativeKernel(prof ? (const void*)k_cg_persistent<true> : (const void*)k_cg_persistent<false>, dim3((unsigned)persistent_grid), dim3(CGP_THREADS), params,
+                                                     sizeof(double) * 2 * (size_t)n, st));
+                launches += 1;
+            }
+            return FNN_OK;
+        }
         if (!cg_graph) {
             cudaGraph_t g;
             const int64_t before = launches;
@@ -806,6 +1284,22 @@ static int solve_split_weights(Csw& c, const fnn_opts* o, const int32_t* orderin
     int rc = c.alloc();
     if (rc) return rc;
     if (c.literal) FNN_CUDA(cudaFuncSetAttribute(lit::k_cg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(xsum::Smem)));
+    if (!c.literal && !(o && o->reserved[4] == 1) && n <= CGP_MAX_N) {   // reserved[4] = 1 keeps the launch-per-phase graph path (A/B)
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        FNN_CUDA(cudaGetDevice(&dev));
+        FNN_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        FNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FNN_CUDA(cudaFuncSetAttribute(k_cg_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * (size_t)n)));
+        FNN_CUDA(cudaFuncSetAttribute(k_cg_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * (size_t)n)));
+        FNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persistent<true>, CGP_THREADS, sizeof(double) * 2 * (size_t)n));
+        per_sm = std::min(per_sm, 1);
+        if (coop && per_sm >= 1) {
+            c.persistent = 1;
+            int64_t want = (c.np + 2047) / 2048;   // >= 4 entries per thread and phase; fewer CTAs = cheaper barriers
+            if (const char* e = getenv("FNN_CSW_GRID")) want = atoll(e);
+            c.persistent_grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * per_sm, want));
+        }
+    }
     int* d_ord = reinterpret_cast<int*>(c.tie_rank);   // scratch: free until the first 60 % collapse
     FNN_CUDA(cudaMemcpyAsync(d_ord, ordering, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c.st));
     FNN_CUDA(cudaMemcpyAsync(c.r, d_upper, sizeof(double) * c.np, d_upper_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
@@ -829,6 +1323,18 @@ static int fetch_stats(Csw& c, int64_t* stats_out) {
     FNN_CUDA(cudaMemcpyAsync(c.h_sc, c.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c.st));
     FNN_CUDA(cudaStreamSynchronize(c.st));
     FNN_CUDA(cudaGetLastError());
+    if (c.prof && c.h_sc->iters_total > 0) {
+        unsigned long long h[24];
+        FNN_CUDA(cudaMemcpy(h, c.prof, sizeof(h), cudaMemcpyDeviceToHost));
+        static const char* nm[19] = {"ph1 pupdate+rowscan", "bar1", "ph2 colscan_local", "bar2", "ph3 carry", "bar3", "ph4 combine+rowscan", "bar4",
+                                     "ph5 colscan_local+CT", "bar5", "ph6 carry+CT", "bar6", "ph7 prs+diag", "ph8 atx combine+dot", "bar7",
+                                     "ph9 reduce alpha", "ph10 xr update", "bar8", "ph11 reduce rho"};
+        double tot = 0;
+        for (int q = 0; q < 19; ++q) tot += (double)h[q];
+        fprintf(stderr, "[fnn] k_cg_persistent n=%d grid=%d: %.2f us per iteration over %lld iterations (CTA 0):\n", c.n, c.persistent_grid,
+                tot / 1e3 / (double)c.h_sc->iters_total, (long long)c.h_sc->iters_total);
+        for (int q = 0; q < 19; ++q) fprintf(stderr, "[fnn]   %-24s %7.2f us\n", nm[q], (double)h[q] / 1e3 / (double)c.h_sc->iters_total);
+    }
     if (stats_out) { stats_out[0] = c.h_sc->iters_total; stats_out[1] = c.cg_calls; stats_out[2] = c.outer; stats_out[3] = c.inner; stats_out[4] = c.launches; }
     return FNN_OK;
 }

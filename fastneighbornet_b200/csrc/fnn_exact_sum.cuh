@@ -36,15 +36,17 @@ constexpr double TWO53 = 9007199254740992.0;
 constexpr unsigned long long M52 = (1ull << 52) - 1;
 constexpr int E_INVALID = 0, E_IDENT = -1;   // summary exponent codes (else: biased exponent 1..2046)
 
-struct Smem {
-    double wtot[4][32];
-    double wC[4][32];
-    int wE[4][32];
-    double cC[4][THREADS];
-    int cE[4][THREADS];
-    double leaf[4][LEAF_BUF];
-    double result[4];
+template <int NR>
+struct SmemN {
+    double wtot[NR][32];
+    double wC[NR][32];
+    int wE[NR][32];
+    double cC[NR][THREADS];
+    int cE[NR][THREADS];
+    double leaf[NR][LEAF_BUF];
+    double result[NR];
 };
+using Smem = SmemN<4>;
 
 // longest applicable prefix of the 32 lane summaries (lanes < start are already consumed).
 // s is uniform across the warp.  Returns the index of the first summary that was NOT applied.
@@ -77,8 +79,8 @@ __device__ __forceinline__ int coop_apply(double& s, int e_lane, double C_lane, 
 // load(r, t, k): element k of segment t (= element t*L + k) of chain r, with L = ceil(len/1024) - callers may store
 // chains segment-transposed so that the 32 lanes of a warp read consecutive addresses; present(r): whether chain r
 // exists; out[r] = sequential sum.
-template <int NR, typename Loader, typename Present>
-__device__ void block_exact_seq_sum(Smem* sm, int len, Loader load, Present present, double* out) {
+template <int NR, typename SmemT, typename Loader, typename Present>
+__device__ void block_exact_seq_sum(SmemT* sm, int len, Loader load, Present present, double* out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = (len + THREADS - 1) / THREADS;            // <= LEAF_MAX
     const int i0 = min(tid * L, len), i1 = min(i0 + L, len);

@@ -209,7 +209,10 @@ __global__ void k_zero_diag(double* D, int64_t ld, int n) {
 // chain r.  Double-buffered so the staging of tile k+1 overlaps the dependent adds of tile k.
 constexpr int CH_TILE = 1024;
 constexpr size_t PICK_SMEM = sizeof(xsum::Smem) > 2 * 4 * CH_TILE * sizeof(double) ? sizeof(xsum::Smem) : 2 * 4 * CH_TILE * sizeof(double);
-constexpr size_t CHAIN_SMEM = PICK_SMEM;
+// k_chain_patch: one chain.  When it fits, the whole staged chain is first copied into shared memory with every load in
+// flight at once (one L2 round trip instead of one per pass / per opened segment of the exact summation).
+constexpr size_t CHAIN_SMEM_BASE = sizeof(xsum::SmemN<1>) > 2 * CH_TILE * sizeof(double) ? sizeof(xsum::SmemN<1>) : 2 * CH_TILE * sizeof(double);
+constexpr size_t CHAIN_SMEM_MAX = 220 * 1024;
 
 template <int NR, typename Loader>
 __device__ void block_seq_sum(double (*buf)[NR][CH_TILE], int len, Loader load, double* out /*[NR]*/) {
@@ -781,8 +784,8 @@ k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevSta
 // same (Q, i, j) key as the scan.  k_rx_stage (after the graph join) merges the two partial min-locs.
 __global__ void __launch_bounds__(PICK_THREADS, 1)
 k_chain_patch(const double* __restrict__ D, int64_t ld, double* Sx, const int* __restrict__ id, const int* __restrict__ pos,
-              const int* __restrict__ p2s, DevState* st, const double* __restrict__ stage, int serial_chain) {
-    extern __shared__ unsigned char smem_raw[];
+              const int* __restrict__ p2s, DevState* st, const double* __restrict__ stage, int serial_chain, int stage_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     double (*buf)[1][CH_TILE] = reinterpret_cast<double (*)[1][CH_TILE]>(smem_raw);
     __shared__ double tot[1];
     __shared__ Partial wbest[PICK_THREADS / 32];
@@ -796,10 +799,25 @@ k_chain_patch(const double* __restrict__ D, int64_t ld, double* Sx, const int* _
     if (tid == 0) tl_stamp(st, TL_CHAIN0);
     if (su >= 0) {
         const int Ln = (m + xsum::THREADS - 1) / xsum::THREADS;
-        auto load_seg = [&](int, int t, int k) -> double { return stage[k * xsum::THREADS + t]; };
         auto load_lin = [&](int, int i) -> double { return stage[(i % Ln) * xsum::THREADS + i / Ln]; };
         if (serial_chain) block_seq_sum<1>(buf, m, load_lin, tot);
-        else xsum::block_exact_seq_sum<1>(reinterpret_cast<xsum::Smem*>(smem_raw), m, load_seg, [](int) { return true; }, tot);
+        else if (Ln * xsum::THREADS <= stage_cap) {
+            // the chain (segment-transposed, Ln x 1024) into shared memory: all of a thread's loads are independent
+            double* sc = reinterpret_cast<double*>(smem_raw + CHAIN_SMEM_BASE);
+            for (int k0 = 0; k0 < Ln; k0 += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (k0 + u < Ln) v[u] = stage[(k0 + u) * xsum::THREADS + tid];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (k0 + u < Ln) sc[(k0 + u) * xsum::THREADS + tid] = v[u];
+            }
+            __syncthreads();
+            auto load_sm = [&](int, int t, int k) -> double { return sc[k * xsum::THREADS + t]; };
+            xsum::block_exact_seq_sum<1>(reinterpret_cast<xsum::SmemN<1>*>(smem_raw), m, load_sm, [](int) { return true; }, tot);
+        } else {
+            auto load_seg = [&](int, int t, int k) -> double { return stage[k * xsum::THREADS + t]; };
+            xsum::block_exact_seq_sum<1>(reinterpret_cast<xsum::SmemN<1>*>(smem_raw), m, load_seg, [](int) { return true; }, tot);
+        }
         const double Su = tot[0];
         if (tid == 0) { Sx[su] = Su; Sx[su + 1] = Su; tl_stamp(st, TL_CHAIN1); }
         if (!strategy && !(m == 4 && st->c == 2)) {
@@ -897,6 +915,8 @@ struct fnn_ctx {
     double* rx_part = nullptr;        // per-block partial ComputeRx sums of k_rx_stage
     int scan_grid = 0, row_grid = 0;
     // u.Sx chain + new-cluster patch on a forked branch, concurrent with the next scan (which then leaves one SM to it)
+    size_t chain_smem = 0;            // k_chain_patch: exact-summation workspace + (if it fits) the staged chain
+    int chain_stage_cap = 0;          // elements of the chain that fit in shared memory (0: read from global)
     bool overlap = false;
     int force_exact = 0;              // A/B: always decide the pick with the exact left-to-right sums
     cudaStream_t stream2 = nullptr;
@@ -1072,7 +1092,12 @@ static int ctx_build(fnn_ctx* c, const fnn_opts* o, int64_t n) {
     FNN_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     FNN_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     FNN_CUDA(cudaFuncSetAttribute(k_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PICK_SMEM));
-    FNN_CUDA(cudaFuncSetAttribute(k_chain_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
+    {
+        const size_t want = CHAIN_SMEM_BASE + sizeof(double) * (size_t)c->rxs_ld;
+        if (want <= CHAIN_SMEM_MAX) { c->chain_smem = want; c->chain_stage_cap = (int)c->rxs_ld; }
+        else { c->chain_smem = CHAIN_SMEM_BASE; c->chain_stage_cap = 0; }
+        FNN_CUDA(cudaFuncSetAttribute(k_chain_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
+    }
     int trc = make_tensor_map(c);
     if (trc) return trc;
     FNN_CUDA(cudaFuncSetAttribute(tma::k_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma::SMEM_BYTES));
@@ -1178,7 +1203,8 @@ static inline void launch_rest(fnn_ctx* c) {
         cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
         cs = c->stream2;
     }
-    k_chain_patch<<<1, PICK_THREADS, CHAIN_SMEM, cs>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->stage, c->serial_chain);
+    k_chain_patch<<<1, PICK_THREADS, c->chain_smem, cs>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->stage, c->serial_chain,
+                                                         c->chain_stage_cap);
     if (c->overlap) { cudaEventRecord(c->ev_join, c->stream2); c->join_pending = true; }
 }
 // the forked branch has to be back on the main stream before a capture ends, before the state is read, before the next run

@@ -84,8 +84,24 @@ void Ab(int64_t n, const double* in, double* out, Work& w) {
 void Atx(int64_t n, const double* in, double* out, Work& w) {
     rowscan(n, in, w.Rw.data(), w.RT.data());
     colscan(n, w.Rw.data(), in, w.P.data(), w.CT.data());
-    double acc = 0.0;
-    for (int64_t a = 0; a < n; ++a) { acc = acc + (w.RT[a] + w.CT[a]); w.PRS[a] = acc; }
+    {   // prs_scan_warp: blocks of 32, Kogge-Stone inside, carry added sequentially
+        double carry = 0.0;
+        for (int64_t blk = 0; blk < n; blk += 32) {
+            double e[32], t[32];
+            for (int l = 0; l < 32; ++l) e[l] = (blk + l < n) ? w.RT[blk + l] + w.CT[blk + l] : 0.0;
+            for (int off = 1; off < 32; off <<= 1) {
+                for (int l = 0; l < 32; ++l) t[l] = (l >= off) ? e[l] + e[l - off] : e[l];
+                for (int l = 0; l < 32; ++l) e[l] = t[l];
+            }
+            double last = 0.0;
+            for (int l = 0; l < 32; ++l) {
+                const double out = carry + e[l];
+                if (blk + l < n) w.PRS[blk + l] = out;
+                if (l == 31) last = out;
+            }
+            carry = last;
+        }
+    }
     const double* G = w.P.data();
     for (int64_t i = 0; i < n - 1; ++i)
         for (int64_t j = i + 1; j < n; ++j) {

@@ -69,3 +69,18 @@ def test_jni_shim_compiles_and_links_against_the_abi(tmp_path):
     assert sorted(natives) == ["network", "order", "orderFromFile", "splitWeights"]
     for name in natives:
         assert f"Java_nnet_NativeNN_{name}" in syms
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference sources are only present in the build container")
+def test_java_patch_applies_to_the_reference(tmp_path):
+    """integration/fastnn_java.patch (the FastNN.java:326-361, 378/391, 401-466 call-site change plus the seeded
+    java.util.Random of NeighborNetLocal.java:30 / NeighborNetRandom.java:27) applies cleanly to the reference as shipped."""
+    import shutil
+    import subprocess
+    for f in ("FastNN.java", "NeighborNetLocal.java", "NeighborNetRandom.java"):
+        shutil.copy(os.path.join("/root/reference", f), tmp_path / f)
+    r = subprocess.run(["patch", "-p1", "-i", os.path.join(ROOT, "integration", "fastnn_java.patch")], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    src = (tmp_path / "FastNN.java").read_text()
+    assert src.count("NativeNN.order(") == 2 and "NativeNN.splitWeights(" in src
