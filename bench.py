@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--csw-n", type=int, default=400, help="taxa of the split-weight config entry")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -431,6 +432,25 @@ def main():
                     "strategy_units": s_["strategy_units"], "ordering_sha256": sha(oo)}
 
         configs.append(timed("configs[0]: Canonical -order, 200-taxon additive tree (eps=0)", 200, 1, 0.0, "scan_alg_bytes"))
+        configs.append(timed("configs[1] ordering stage: Canonical, 5000 taxa", 5000, 2, 0.05, "scan_alg_bytes"))
+        # configs[1] split-weight stage (CircularSplitWeights active-set + CG) at the size that fits the step budget; the roofline of
+        # ONE CG iteration is SURVEY 8(d)'s 112 * npairs algorithmic bytes / measured time per iteration
+        csn = args.csw_n
+        Dc = synth.additive_noise_matrix(csn, 1, 0.05)
+        oc = fnn.order(Dc, device=local_rank)
+        duc = synth.upper_triangle(Dc)
+        fnn.split_weights(oc, duc, constrained=False, device=local_rank)   # warm-up
+        t0_ = time.perf_counter()
+        xc, stc = fnn.split_weights(oc, duc, device=local_rank)
+        dtc = time.perf_counter() - t0_
+        npairs = csn * (csn - 1) // 2
+        us_it = 1e6 * dtc / max(1, stc["cg_iters"])
+        configs.append({"config": f"configs[1] split-weight stage at the size that fits the step budget: CircularSplitWeights (active set + CG), {csn} taxa",
+                        "n_taxa": csn, "ms": 1e3 * dtc, "cg_iterations": stc["cg_iters"], "cg_solves": stc["cg_calls"], "us_per_cg_iteration": us_it,
+                        "alg_bytes_per_cg_iteration": 112.0 * npairs, "achieved": 112.0 * npairs / (us_it * 1e-6) / 1e9, "unit": "GB/s",
+                        "frac": 112.0 * npairs / (us_it * 1e-6) / 1e9 / peak, "gpu_launches": stc["kernel_launches"], "kept_splits": int((xc > 1e-6).sum()),
+                        "bound": "barrier/L2 latency at this size (8 grid barriers per iteration, DESIGN.md 4.3), HBM only above n ~ 3000"})
+        fnn.release_cache()
         configs.append(timed("configs[2] without -additive: Relaxed, 20000 taxa (row scans: SURVEY 8d K7 bytes + the canonical tail's scan bytes)",
                              20000, 3, 0.05, "strategy_alg_bytes", mode="relaxed", seed=7))
         configs.append(timed("configs[3] at the size that fits the step budget: Random_NLOGN -mult 5, 10000 taxa (samples: SURVEY 8d K9 bytes + tail scan bytes)",

@@ -420,11 +420,14 @@ constexpr int CGP_THREADS = 512;          // 128 registers per thread: the phase
 constexpr int CGP_Q = CGP_THREADS / 256;    // 256-thread groups, each owns one 1024-entry block of the reduction tree
 constexpr int CGP_MAX_N = 12000;            // two n-vectors of doubles in shared memory (PRS / diagonal, row ends)
 
-// Cross-CTA data is read with ld.global.cg (L2, never this SM's L1): coherent across the grid barriers without relying on
-// L1 invalidation, and - being explicit loads from buffers the compiler cannot prove read-only - free to be hoisted above
-// the stores of the same phase, which go to other buffers.  That hoisting is the point: every phase is a few ROUNDS of
-// independent loads (~0.7 us L2 latency each), not a chain of dependent ones.
-__device__ __forceinline__ double ldg_cg(const double* p) { return __ldcg(p); }
+// Every phase is written as a few ROUNDS of independent loads (each thread first issues all loads of a small batch, then
+// consumes them) instead of a chain of dependent ones: the solver is latency-bound at the sizes it is used at.  Batches are
+// sized so that nothing spills: a spill store waits for its load and, issue being in order, serialises the whole batch
+// (ncu, round 2: STL.64 with long-scoreboard stalls were the hot instructions of a 16-deep version).
+// Cross-CTA data is read with ordinary (L1-cached) loads: the acquire of every grid barrier invalidates this SM's L1
+// (SASS CCTL.IVALL), nothing is exchanged inside a phase, and per-thread runs of 4 consecutive doubles then cost one L2
+// sector fetch instead of four (ld.global.cg made phases 8 and 10 L2-bandwidth-bound: x4 sector traffic).
+__device__ __forceinline__ double ldg_cg(const double* p) { return *p; }
 
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long nblocks, unsigned long long& gen) {
     __syncthreads();
@@ -435,10 +438,10 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
         if (prev + 1 == nblocks * gen) {
             asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&bar[1]), "l"(gen) : "memory");
         } else {
-            unsigned long long g;
-            do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(&bar[1]) : "memory"); } while (g < gen);
+            unsigned long long g;   // relaxed polls (an acquire load invalidates L1 on every poll), one acquire fence at the end
+            do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(&bar[1]) : "memory"); } while (g < gen);
         }
-        __threadfence();
+        __threadfence();   // acquire side: orders the phase's loads after the release and drops this SM's stale L1 lines
     }
     __syncthreads();
 }
@@ -512,7 +515,7 @@ __device__ __forceinline__ void colscan_local_thread(const double* Rw, const dou
     const int i0 = c * COL_CHUNK, i1 = min(i0 + COL_CHUNK, j);
     double acc = 0.0, acc2 = 0.0;
     int64_t q = (i0 < i1) ? pidx(n, i0, j) : 0;
-    constexpr int B = WITH_CT ? 8 : 16;
+    constexpr int B = WITH_CT ? 4 : 8;
     for (int h0 = i0; h0 < i1; h0 += B) {
         double rw[B], vv[WITH_CT ? B : 1];
         int64_t qq = q;
@@ -544,7 +547,7 @@ __device__ __forceinline__ void colscan_local_thread(const double* Rw, const dou
 template <bool WITH_CT>
 __device__ __forceinline__ void colscan_carry_thread(double* T, const double* T2, double* CT, int n, int nchunks, int j) {
     double carry = 0.0, acc2 = 0.0;
-    constexpr int B = WITH_CT ? 8 : 16;
+    constexpr int B = WITH_CT ? 4 : 8;
     for (int c0 = 0; c0 < nchunks; c0 += B) {
         double t[B], t2[WITH_CT ? B : 1];
 #pragma unroll
@@ -575,7 +578,8 @@ __global__ void __launch_bounds__(CGP_THREADS, 1) k_cg_persistent(CgArgs a) {
     double* vecB = dyn + n;
     const long long np = a.np, nblk = a.nblk;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int gwarp = blockIdx.x * (CGP_THREADS / 32) + (tid >> 5), nwarps = gridDim.x * (CGP_THREADS / 32);
+    // rows are dealt round-robin over the CTAs (row i -> CTA i % grid): the long rows (small i) bound the row-scan phases
+    const int gwarp = (tid >> 5) * gridDim.x + blockIdx.x, nwarps = gridDim.x * (CGP_THREADS / 32);
     const long long gtid = (long long)blockIdx.x * CGP_THREADS + tid, gthreads = (long long)gridDim.x * CGP_THREADS;
     const int g = tid >> 8, t4 = tid & 255;
     const unsigned long long nblocks = gridDim.x;
@@ -589,7 +593,7 @@ __global__ void __launch_bounds__(CGP_THREADS, 1) k_cg_persistent(CgArgs a) {
     const long long kmax = a.sc->kmax;
     int done = a.sc->done;
     long long left = a.max_iters;
-    constexpr int U = 8;   // 32-element blocks of a row in flight per warp
+    constexpr int U = 4;   // 32-element blocks of a row in flight per warp
     unsigned long long tacc[PROF ? 20 : 1], tlast = 0;
     const bool prof = PROF && (a.prof != nullptr) && gtid == 0;
     if (PROF && prof) {
@@ -715,15 +719,19 @@ __global__ void __launch_bounds__(CGP_THREADS, 1) k_cg_persistent(CgArgs a) {
         grid_barrier(a.bar, nblocks, gen);
         CG_MARK(11)
         // ---- phase 7 (per CTA): k_prs -> vecA; vecB[j] = G(j,j) = fixed G at (j-1, j)
-        if (tid < 32) {
+        for (int j = tid; j < n; j += CGP_THREADS) {   // operands first (every load of the CTA in flight at once) ...
+            vecA[j] = ldg_cg(a.RT + j) + ldg_cg(a.CT + j);
+            vecB[j] = (j >= 1) ? fixed_P(a.P, a.T, n, j - 1, j) : 0.0;
+        }
+        __syncthreads();
+        if (tid < 32) {                                // ... then the blocked scan in place, from shared memory
             double carry = 0.0;
             for (int blk = 0; blk < n; blk += 32) {
-                const double e = (blk + lane < n) ? ldg_cg(a.RT + blk + lane) + ldg_cg(a.CT + blk + lane) : 0.0;
+                const double e = (blk + lane < n) ? vecA[blk + lane] : 0.0;
                 const double out = scan32_carry(e, carry, lane);
                 if (blk + lane < n) vecA[blk + lane] = out;
             }
         }
-        for (int j = tid; j < n; j += CGP_THREADS) vecB[j] = (j >= 1) ? fixed_P(a.P, a.T, n, j - 1, j) : 0.0;
         __syncthreads();
         CG_MARK(12)
         // ---- phase 8: w = mask(A^T y), partial products p.w   (k_atx_combine<1>, fix folded in)
@@ -737,32 +745,21 @@ __global__ void __launch_bounds__(CGP_THREADS, 1) k_cg_persistent(CgArgs a) {
                 while (i > 0 && row_start(n, i) > base) --i;
                 while (row_start(n, i + 1) <= base) ++i;
                 int64_t j = base - row_start(n, i) + i + 1;
-                double tc[4], pl[4], pp[4];
-                int ii[4], jj[4];
-                bool act[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int64_t kk = base + q;
-                    ii[q] = (int)i; jj[q] = (int)j;
-                    if (kk < np) {
-                        tc[q] = ldg_cg(a.T + (int64_t)((int)i / COL_CHUNK) * n + j);
-                        pl[q] = ldg_cg(a.P + kk);
-                        pp[q] = ldg_cg(a.p + kk);
-                        act[q] = a.active[kk] != 0;
-                        if (++j == n) { ++i; j = i + 1; }
-                    }
-                }
+                // a thread's 4 consecutive entries share one 32-byte sector per array: the q = 0 loads go to L2, the rest hit L1
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int64_t kk = base + q;
                     if (kk < np) {
-                        const double u = vecA[jj[q]] - vecA[ii[q]];
-                        const double Gij = tc[q] + pl[q];
-                        const double wv = vecB[jj[q]] - Gij;
+                        const double Gij = ldg_cg(a.T + (int64_t)((int)i / COL_CHUNK) * n + j) + ldg_cg(a.P + kk);
+                        const double pk = ldg_cg(a.p + kk);
+                        const bool act = a.active[kk] != 0;
+                        const double u = vecA[j] - vecA[i];
+                        const double wv = vecB[j] - Gij;
                         double pv = u - 2.0 * wv;
-                        if (act[q]) pv = 0.0;
-                        prod[q] = pp[q] * pv;
+                        if (act) pv = 0.0;
+                        prod[q] = pk * pv;
                         a.w[kk] = pv;
+                        if (++j == n) { ++i; j = i + 1; }
                     }
                 }
             }
@@ -792,21 +789,29 @@ __global__ void __launch_bounds__(CGP_THREADS, 1) k_cg_persistent(CgArgs a) {
             const int64_t base = (int64_t)vb * 1024 + 4 * t4;
             double e[4] = {0.0, 0.0, 0.0, 0.0};
             if (valid) {
-                double xv[4], pv[4], rv[4], wv[4];
+                if (base + 3 < np) {   // 16-byte loads first (base is a multiple of 4: aligned), then the stores
+                    const double2 x0 = *reinterpret_cast<const double2*>(a.x + base), x1 = *reinterpret_cast<const double2*>(a.x + base + 2);
+                    const double2 p0 = *reinterpret_cast<const double2*>(a.p + base), p1 = *reinterpret_cast<const double2*>(a.p + base + 2);
+                    const double2 r0 = *reinterpret_cast<const double2*>(a.r + base), r1 = *reinterpret_cast<const double2*>(a.r + base + 2);
+                    const double2 w0 = *reinterpret_cast<const double2*>(a.w + base), w1 = *reinterpret_cast<const double2*>(a.w + base + 2);
+                    double2 nx0, nx1, nr0, nr1;
+                    nx0.x = x0.x + alpha * p0.x; nx0.y = x0.y + alpha * p0.y; nx1.x = x1.x + alpha * p1.x; nx1.y = x1.y + alpha * p1.y;
+                    nr0.x = r0.x - alpha * w0.x; nr0.y = r0.y - alpha * w0.y; nr1.x = r1.x - alpha * w1.x; nr1.y = r1.y - alpha * w1.y;
+                    *reinterpret_cast<double2*>(a.x + base) = nx0; *reinterpret_cast<double2*>(a.x + base + 2) = nx1;
+                    *reinterpret_cast<double2*>(a.r + base) = nr0; *reinterpret_cast<double2*>(a.r + base + 2) = nr1;
+                    e[0] = nr0.x * nr0.x; e[1] = nr0.y * nr0.y; e[2] = nr1.x * nr1.x; e[3] = nr1.y * nr1.y;
+                } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (base + q < np) {
-                        xv[q] = ldg_cg(a.x + base + q); pv[q] = ldg_cg(a.p + base + q);
-                        rv[q] = ldg_cg(a.r + base + q); wv[q] = ldg_cg(a.w + base + q);
-                    }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (base + q < np) {
-                        a.x[base + q] = xv[q] + alpha * pv[q];
-                        const double nr = rv[q] - alpha * wv[q];
-                        a.r[base + q] = nr;
-                        e[q] = nr * nr;
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        if (base + q < np) {
+                            const double xv = ldg_cg(a.x + base + q), pv = ldg_cg(a.p + base + q);
+                            const double rv = ldg_cg(a.r + base + q), wv = ldg_cg(a.w + base + q);
+                            a.x[base + q] = xv + alpha * pv;
+                            const double nr = rv - alpha * wv;
+                            a.r[base + q] = nr;
+                            e[q] = nr * nr;
+                        }
+                }
             }
             double s = ((e[0] + e[1]) + e[2]) + e[3];
 #pragma unroll
@@ -1102,7 +1107,8 @@ struct Csw {
         launches += 1;
         if (persistent) {
             // bounded launches (the kernel is resumable: all loop state lives in Scalars and the barrier words)
-            const long long per_launch = 1 << 16;
+            long long per_launch = 1 << 16;
+            if (const char* e = getenv("FNN_CSW_ITERS_PER_LAUNCH")) per_launch = std::max<long long>(1, atoll(e));   // profiling sessions
             FNN_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned long long), st));
             while (true) {
                 FNN_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));

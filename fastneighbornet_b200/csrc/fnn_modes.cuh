@@ -102,6 +102,7 @@ k_random_walk(const int* __restrict__ pos, const int* __restrict__ p2s, DevState
     __shared__ long long s_count;
     const int m = st->m, P2 = st->P2, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long total = random_search_amount(st->mode, st->mult, m);
+    if (tid == 0) tl_stamp(st, TL_SCAN0);
     // neighbour position per position (-1: singleton), shared by this kernel's parallel lookups
     for (int i = tid; i < m; i += THREADS) {
         const int s = p2s[i];
@@ -290,6 +291,7 @@ k_random_eval(const double* __restrict__ D, int64_t ld, const double* __restrict
         st->cy_pos = pr.y;
         st->strat_units += (unsigned long long)total;
         *ticket = 0;
+        tl_stamp(st, TL_SCAN1);
     }
 }
 
@@ -306,14 +308,48 @@ __device__ int block_rowmin(const double* __restrict__ D, int64_t ld, const doub
     const int sp = p2s[ip];
     const int spn = sp < P2 ? (sp ^ 1) : -1;
     const double Sp = Sx[sp];
+    const double* rp = D + (int64_t)sp * ld;
+    const double* rpn = spn >= 0 ? D + (int64_t)spn * ld : rp;
+    // Q(p, q) with p first (calculateDpq, NeighborNetLocal.java:266-278), every operand of a group of RU candidates loaded
+    // before the first use: a row scan is a handful of rounds of independent loads, not one round per candidate
+    constexpr int RU = 4;
+    auto q_of = [&](int sq, double a, double b, double c2, double d2, double Sq) -> double {
+        const bool qp = sq < P2;
+        double dpq;
+        if (spn < 0 && !qp) dpq = a;
+        else if (spn >= 0 && !qp) dpq = (a + c2) * 0.5;          // (D[p][q] + D[p.nbr][q]) / 2
+        else if (spn < 0) dpq = (a + b) * 0.5;                    // (D[p][q] + D[p][q.nbr]) / 2
+        else dpq = (((a + b) + c2) + d2) * 0.25;                  // D[p][q] + D[p][q.nbr] + D[p.nbr][q] + D[p.nbr][q.nbr]
+        return (cm2 * dpq - Sp) - Sq;
+    };
+    // the minimum and the SET of its ties do not depend on the visiting order, so the block walks physical slots
+    // (coalesced rows) and orders the ties by position afterwards.  One pass: every thread keeps its minimum, the first
+    // slot that reached it and how many of its candidates tie with it.
     double mn = INFINITY;
-    // every active q except p and p.nbr (:100-105).  The minimum and the SET of its ties do not depend on the visiting
-    // order, so the block walks physical slots (coalesced rows) and orders the ties by position afterwards.
-    for (int sq = tid; sq < m; sq += THREADS) {
-        if (sq == sp || sq == spn) continue;
-        const double q = (cm2 * dpq_roles(D, ld, sp, sq, P2) - Sp) - Sx[sq];
-        mn = fmin(mn, q);
+    int first_sq = -1, neq = 0;
+    for (int s0 = tid; s0 < m; s0 += RU * THREADS) {
+        double a[RU], b[RU], c2[RU], d2[RU], Sq[RU];
+        bool use[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int sq = s0 + u * THREADS;
+            use[u] = sq < m && sq != sp && sq != spn;           // every active q except p and p.nbr (:100-105)
+            a[u] = b[u] = c2[u] = d2[u] = Sq[u] = 0.0;
+            if (use[u]) {
+                const int sqn = sq < P2 ? (sq ^ 1) : sq;
+                Sq[u] = Sx[sq]; a[u] = rp[sq]; b[u] = rp[sqn]; c2[u] = rpn[sq]; d2[u] = rpn[sqn];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            if (!use[u]) continue;
+            const int sq = s0 + u * THREADS;
+            const double q = q_of(sq, a[u], b[u], c2[u], d2[u], Sq[u]);
+            if (q < mn) { mn = q; first_sq = sq; neq = 1; }
+            else if (q == mn) { if (first_sq < 0) first_sq = sq; ++neq; }
+        }
     }
+    const double mine = mn;
     for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
     if ((tid & 31) == 0) wmin[tid >> 5] = mn;
     if (tid == 0) cnt = 0;
@@ -325,12 +361,20 @@ __device__ int block_rowmin(const double* __restrict__ D, int64_t ld, const doub
     }
     __syncthreads();
     const double g = gmin;
-    for (int sq = tid; sq < m; sq += THREADS) {   // all exact ties (:118-124), gathered then ordered by position
-        if (sq == sp || sq == spn) continue;
-        const double q = (cm2 * dpq_roles(D, ld, sp, sq, P2) - Sp) - Sx[sq];
-        if (q == g) {
+    if (first_sq >= 0 && mine == g) {   // all exact ties (:118-124), gathered then ordered by position
+        if (neq == 1) {
             const int k = atomicAdd(&cnt, 1);
-            if (k < MAX_TIES) spos[k] = pos[sq];
+            if (k < MAX_TIES) spos[k] = pos[first_sq];
+        } else {                         // several ties inside this thread's candidates: walk them again
+            for (int sq = tid; sq < m; sq += THREADS) {
+                if (sq == sp || sq == spn) continue;
+                const int sqn = sq < P2 ? (sq ^ 1) : sq;
+                const double q = q_of(sq, rp[sq], rp[sqn], rpn[sq], rpn[sqn], Sx[sq]);
+                if (q == g) {
+                    const int k = atomicAdd(&cnt, 1);
+                    if (k < MAX_TIES) spos[k] = pos[sq];
+                }
+            }
         }
     }
     __syncthreads();
@@ -465,6 +509,7 @@ k_relaxed_select(const double* __restrict__ D, int64_t ld, const double* __restr
     const double cm2 = (double)c - 2.0;
     const DevNodeView nv{id, pos, p2s, m, P2};
     if (tid == 0) {
+        tl_stamp(st, TL_SCAN0);   // timeline: the strategy kernel takes the scan's slots while m > fallback
         M = *Mg;
         relaxed::begin_call(M, ntax);
         look_accept = 0;
@@ -497,6 +542,7 @@ k_relaxed_select(const double* __restrict__ D, int64_t ld, const double* __restr
         st->cy_pos = M.cy_pos;
         if (M.error || M.cx_pos < 0 || M.cy_pos < 0) { st->error = 10 + M.error; st->done = 1; st->skip = 1; }
         *Mg = M;
+        tl_stamp(st, TL_SCAN1);
     }
 }
 
