@@ -145,7 +145,7 @@ def workload_config(args, world):
     }
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit=None):
     """--impl reference: the reference's own CPU algorithm (restatement; the JAR needs a JVM that this image does not have).
     Each step = one canonical ordering of a BOUNDED SAMPLE (n = --ref-n) of the workload with all host threads
     (NeighborNetCanonical's thread partition, NeighborNetCanonical.java:180-206); rank 0 only.  The line says which n it ran
@@ -196,7 +196,7 @@ def run_reference(args, rank, world):
                           "seconds_at_workload_n": c_1t * args.n ** 3, "seconds_at_100k": c_1t * 1e15},
         },
     }
-    print(json.dumps(line), flush=True)
+    (emit or (lambda l: print(json.dumps(l), flush=True)))(line)
 
 
 def main():
@@ -220,8 +220,16 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import numpy as np
@@ -480,7 +488,7 @@ def main():
         "picks": {"certified": picks[0], "exact_sums": picks[1]},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "configs": configs,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -65,7 +65,8 @@ ABI_SYMBOLS = [
 
 
 def lib_path():
-    return os.path.join(_HERE, "libfastnn.so")
+    # FNN_LIB: an alternative build of the same library (e.g. one compiled with -DFNN_XSUM_TIMING for a profiling session)
+    return os.environ.get("FNN_LIB") or os.path.join(_HERE, "libfastnn.so")
 
 
 def lib():

@@ -33,6 +33,9 @@ struct DevEvent {
 // internal accessors across translation units (not part of the ABI)
 int64_t fnn_ctx_n_(fnn_ctx* c);
 void fnn_ctx_mark_loaded_(fnn_ctx* c);
+int fnn_ctx_device_(fnn_ctx* c);
+int fnn_ctx_sms_(fnn_ctx* c);
+cudaStream_t fnn_ctx_stream_(fnn_ctx* c);
 
 // CUDA errors are fatal for the call (no CPU fallback): record and return FNN_E_CUDA.
 #define FNN_CUDA(call)                                                                          \

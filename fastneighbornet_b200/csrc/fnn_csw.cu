@@ -1444,9 +1444,10 @@ extern "C" int fnn_network(const fnn_opts* o, const double* D_rowmajor, int64_t 
         fnn_ctx_matrix_ptr(ctx, &dD, &ld);
         const int64_t np = n * (n - 1) / 2;
         FNN_CUDA(cudaMalloc((void**)&d_upper, sizeof(double) * np));
-        k_pack_upper<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 64)), (unsigned)(n - 1)), 256>>>(dD, ld, (int)n, d_upper);
+        cudaStream_t cs = fnn_ctx_stream_(ctx);
+        k_pack_upper<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 64)), (unsigned)(n - 1)), 256, 0, cs>>>(dD, ld, (int)n, d_upper);
         FNN_CUDA(cudaGetLastError());
-        FNN_CUDA(cudaDeviceSynchronize());
+        FNN_CUDA(cudaStreamSynchronize(cs));
         r = fnn_ctx_order(ctx, ordering_out);
         return r;
     }();

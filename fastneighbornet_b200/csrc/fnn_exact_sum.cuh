@@ -198,6 +198,9 @@ __device__ void block_exact_seq_sum(SmemT* sm, int len, Loader load, Present pre
             const double wc = sm->wC[r][lane];
             // sequential adds of elements [j0, j1) staged through shared memory (s stays uniform across the warp)
             auto leaf_sum = [&](int j0, int j1) {
+#ifdef FNN_XSUM_TIMING
+                nleaf_ += j1 - j0;
+#endif
                 for (int k = lane; k < j1 - j0; k += 32) sm->leaf[r][k] = load(r, (j0 + k) / L, (j0 + k) % L);
                 __syncwarp();
                 const double* e = sm->leaf[r];
@@ -214,6 +217,9 @@ __device__ void block_exact_seq_sum(SmemT* sm, int len, Loader load, Present pre
                 const int te = sm->cE[r][w * 32 + lane];
                 const double tc = sm->cC[r][w * 32 + lane];
                 while (s1 < 32) {
+#ifdef FNN_XSUM_TIMING
+                    ++ncoop_;
+#endif
                     s1 = coop_apply(s, te, tc, s1, lane);
                     if (s1 >= 32) break;
                     const int t = w * 32 + s1;
@@ -225,9 +231,16 @@ __device__ void block_exact_seq_sum(SmemT* sm, int len, Loader load, Present pre
             // so the first segments are never collapsible - add them sequentially in one go
             const int S0 = min(32, (PROLOGUE + L - 1) / L);
             leaf_sum(0, min(S0 * L, len));
+#ifdef FNN_XSUM_TIMING
+            const long long tp_ = clock64();
+            if (lane == 0) printf("chain %d: prologue %lld cycles\n", r, tp_ - t2_);
+#endif
             open_warp(0, S0);
             int s2 = 1;
             while (s2 < 32) {
+#ifdef FNN_XSUM_TIMING
+                ++ncoop_;
+#endif
                 s2 = coop_apply(s, we, wc, s2, lane);
                 if (s2 >= 32) break;
                 open_warp(s2, 0);
@@ -236,7 +249,7 @@ __device__ void block_exact_seq_sum(SmemT* sm, int len, Loader load, Present pre
         }
         if (lane == 0) sm->result[r] = s;
 #ifdef FNN_XSUM_TIMING
-        if (lane == 0) printf("chain %d: A1=%lld A2=%lld walk=%lld cycles, coop=%d leaf=%d L=%d\n", r, t1_ - t0_, t2_ - t1_, clock64() - t2_, ncoop_, nleaf_, L);
+        if (lane == 0) printf("chain %d: A1=%lld A2=%lld walk=%lld cycles, coop steps=%d leaf elements=%d L=%d\n", r, t1_ - t0_, t2_ - t1_, clock64() - t2_, ncoop_, nleaf_, L);
 #endif
     }
     __syncthreads();

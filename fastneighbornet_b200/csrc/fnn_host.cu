@@ -108,6 +108,8 @@ __global__ void k_synth(double* D, int64_t ld, int n, const double* __restrict__
 extern "C" int fnn_ctx_synth(fnn_ctx* c, const double* h, const double* a, const int64_t* slot_of_taxon,
                              uint64_t noise_base, double eps) {
     if (!c || !h || !a || !slot_of_taxon) { fnn::set_error("fnn_ctx_synth: null argument"); return FNN_E_ARG; }
+    FNN_CUDA(cudaSetDevice(fnn_ctx_device_(c)));   // a process may hold contexts on several devices
+    cudaStream_t stream = fnn_ctx_stream_(c);
     double* dD; int64_t ld;
     fnn_ctx_matrix_ptr(c, &dD, &ld);
     const int64_t n = fnn_ctx_n_(c);
@@ -126,12 +128,12 @@ extern "C" int fnn_ctx_synth(fnn_ctx* c, const double* h, const double* a, const
     FNN_CUDA(scratch.alloc((void**)&d_tab, tab.size() * sizeof(double)));
     FNN_CUDA(scratch.alloc((void**)&d_a, n * sizeof(double)));
     FNN_CUDA(scratch.alloc((void**)&d_slot, n * sizeof(int)));
-    FNN_CUDA(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-    FNN_CUDA(cudaMemcpy(d_a, a, n * sizeof(double), cudaMemcpyHostToDevice));
-    FNN_CUDA(cudaMemcpy(d_slot, slot.data(), n * sizeof(int), cudaMemcpyHostToDevice));
-    k_synth<<<148 * 8, 256>>>(dD, ld, (int)n, d_tab, d_a, d_slot, noise_base, eps);
+    FNN_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    FNN_CUDA(cudaMemcpyAsync(d_a, a, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    FNN_CUDA(cudaMemcpyAsync(d_slot, slot.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
+    k_synth<<<fnn_ctx_sms_(c) * 8, 256, 0, stream>>>(dD, ld, (int)n, d_tab, d_a, d_slot, noise_base, eps);
     FNN_CUDA(cudaGetLastError());
-    FNN_CUDA(cudaDeviceSynchronize());
+    FNN_CUDA(cudaStreamSynchronize(stream));
     fnn_ctx_mark_loaded_(c);
     return FNN_OK;
 }

@@ -933,6 +933,7 @@ struct fnn_ctx {
     PeerTable* peers = nullptr;       // device table of every rank's mailbox (own entry = mail)
     void* opened[MAX_WORLD] = {nullptr};
     cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t graph_strategy = nullptr;   // Relaxed/Random while m > fallback: the same iterations without the (no-op) scan launch
     int graph_iters = 0;
     unsigned long long* tl = nullptr;  // debug timeline (FNN_TIMELINE)
     int tl_iter0 = 0, tl_count = 0;
@@ -979,6 +980,7 @@ extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->o.device);
     if (c->graph) cudaGraphExecDestroy(c->graph);
+    if (c->graph_strategy) cudaGraphExecDestroy(c->graph_strategy);
     cudaFree(c->rl_machine); cudaFree(c->rl_rowPerm); cudaFree(c->rl_epoch); cudaFree(c->rl_clist); cudaFree(c->rl_loff);
     cudaFree(c->rl_lcnt); cudaFree(c->rl_lme); cudaFree(c->rl_tie); cudaFree(c->rl_mymin);
     cudaFree(c->D); cudaFree(c->Sx); cudaFree(c->scratch); cudaFree(c->stage); cudaFree(c->rxs); cudaFree(c->trace);
@@ -1322,17 +1324,31 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
             FNN_CUDA(cudaGraphInstantiate(&c->graph, g, 0));
             cudaGraphDestroy(g);
             c->graph_iters = GI;
+            if (c->o.mode != FNN_CANONICAL) {
+                FNN_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                for (int i = 0; i < GI; ++i) launch_rest(c);
+                join_branch(c);
+                FNN_CUDA(cudaStreamEndCapture(c->stream, &g));
+                FNN_CUDA(cudaGraphInstantiate(&c->graph_strategy, g, 0));
+                cudaGraphDestroy(g);
+            }
         }
         int64_t it = 0;
+        int64_t m_known = n;   // active nodes at the last poll; an iteration removes at most 2
         while (it < max_iters) {
-            const int64_t batch = 64;  // graphs between done-flag polls
+            // graphs between done-flag polls.  While every iteration of the batch is certain to run the strategy
+            // (m > fallback throughout), the graph without the no-op canonical scan launch is replayed.
+            const int64_t batch = c->graph_strategy ? 16 : 64;
+            const bool strategy_only = c->graph_strategy && (m_known - 2 * batch * GI > (int64_t)c->o.canonical_fallback);
             for (int64_t b = 0; b < batch && it < max_iters; ++b, it += GI) {
-                FNN_CUDA(cudaGraphLaunch(c->graph, c->stream));
-                launches += (int64_t)c->launches_per_iter() * GI; scans += GI;
+                FNN_CUDA(cudaGraphLaunch(strategy_only ? c->graph_strategy : c->graph, c->stream));
+                launches += (int64_t)(c->launches_per_iter() - (strategy_only ? 1 : 0)) * GI;
+                if (!strategy_only) scans += GI;
             }
             FNN_CUDA(cudaMemcpyAsync(c->h_st, c->st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
             FNN_CUDA(cudaStreamSynchronize(c->stream));
             if (c->h_st->done) break;
+            m_known = c->h_st->m;
         }
     } else {
         int64_t it = 0;
@@ -1406,6 +1422,7 @@ extern "C" int fnn_ctx_order(fnn_ctx* c, int32_t* ordering) {
 
 extern "C" int64_t fnn_ctx_trace(fnn_ctx* c, double* rows, int64_t max_rows) {
     if (!c || !rows || !c->trace) { fnn::set_error("fnn_ctx_trace: trace not recorded (opts.record_trace)"); return FNN_E_STATE; }
+    cudaSetDevice(c->o.device);
     int64_t k = std::min<int64_t>(c->trace_rows, max_rows);
     if (cudaMemcpy(rows, c->trace, sizeof(double) * 8 * k, cudaMemcpyDeviceToHost) != cudaSuccess) {
         fnn::set_error("trace copy failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1440,6 +1457,9 @@ extern "C" int fnn_rowsums(const fnn_opts* o, const double* Dh, int64_t n, doubl
 // internal accessors for the other translation units of the library (not part of the ABI)
 int64_t fnn_ctx_n_(fnn_ctx* c) { return c->n; }
 void fnn_ctx_mark_loaded_(fnn_ctx* c) { c->loaded = true; }
+int fnn_ctx_device_(fnn_ctx* c) { return c->o.device; }
+int fnn_ctx_sms_(fnn_ctx* c) { return c->sms; }
+cudaStream_t fnn_ctx_stream_(fnn_ctx* c) { return c->stream; }
 
 extern "C" int fnn_seq_sum(const fnn_opts* o, const double* rows, int32_t nrows, int64_t len, double* out) {
     if (!rows || !out || nrows < 1 || nrows > 4 || len < 0 || len > (int64_t)xsum::THREADS * xsum::LEAF_MAX) { fnn::set_error("fnn_seq_sum: bad arguments"); return FNN_E_ARG; }
@@ -1504,5 +1524,6 @@ extern "C" int fnn_ctx_connect(fnn_ctx* c, int32_t rank, int32_t world, const vo
     c->rank = rank;
     c->world = world;
     if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+    if (c->graph_strategy) { cudaGraphExecDestroy(c->graph_strategy); c->graph_strategy = nullptr; }
     return FNN_OK;
 }

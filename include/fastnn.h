@@ -32,6 +32,12 @@ extern "C" {
 #define FNN_E_IO (-6)
 #define FNN_E_UNSUPPORTED (-7)
 
+/* Capacity limits of the Relaxed strategy (the reference's ArrayLists grow without bound): one row scan may return at most
+ * 4096 exact ties of the row minimum, one findNodes call may cache at most 16 n + 65536 tie entries and 8 n + 65536
+ * candidate pairs.  Beyond that (a constant matrix or thousands of duplicate taxa with n in the thousands) the ordering
+ * stops with FNN_E_STATE (device-side code 11-13) instead of returning a wrong result; Canonical and Random have no such
+ * limit. */
+
 /* NetMakerOriginal.NMMode (NetMakerOriginal.java:19-21) */
 enum fnn_mode {
     FNN_CANONICAL = 0,

@@ -32,5 +32,8 @@ struct JNINativeInterface_ {
     void (*SetIntArrayRegion)(JNIEnv*, jintArray, jsize, jsize, const jint*);
     void (*GetDoubleArrayRegion)(JNIEnv*, jdoubleArray, jsize, jsize, jdouble*);
     void (*SetDoubleArrayRegion)(JNIEnv*, jdoubleArray, jsize, jsize, const jdouble*);
+    jboolean (*ExceptionCheck)(JNIEnv*);
+    jsize (*GetArrayLength)(JNIEnv*, jarray);
 };
+typedef struct JavaVM_ JavaVM;
 #endif

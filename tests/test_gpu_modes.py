@@ -77,3 +77,18 @@ def test_random_n3000_exercises_rejections(fnn):
     """~3e7 draws: dozens of nextInt rejections and hundreds of i/i.nbr remaps must be replayed exactly by the
     speculative parallel walk (k_random_walk)."""
     _check(fnn, tree_matrix(3000, 6, 0.05), "random_n", seed=2024, fallback=1024)
+
+
+def test_relaxed_tie_heavy_matrices(fnn):
+    """Every candidate of every row ties exactly (constant matrix) / blocks of duplicate taxa: the row scans return long tie
+    lists (position order), the mutual-nearest test walks them, and the pools stay inside their documented capacity
+    (include/fastnn.h).  Trace-exact against the oracle."""
+    n = 120
+    const = np.ones((n, n)) - np.eye(n)
+    rng = np.random.default_rng(3)
+    base = tree_matrix(30, 2, 0.05)
+    idx = np.repeat(np.arange(30), 4)            # 4 copies of each of 30 taxa: zero distances inside a block
+    dup = base[np.ix_(idx, idx)]
+    for D in (const, dup):
+        _check(fnn, D, "relaxed", seed=11)
+        _check(fnn, D, "random_n", seed=11)
