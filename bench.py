@@ -364,7 +364,7 @@ def main():
         def e2e_step():
             if world == 1:
                 return fnn.order(Dh, device=local_rank)   # the one-shot reference-facing seam (fnn_order)
-            ctx.load_host(Dh)                             # N>1: same public API on the wired context
+            ctx.load_host_sharded(Dh)                     # N>1: each rank uploads 1/world of the rows, NVLink does the rest
             return ctx.order()
 
         if world == 1:
@@ -381,7 +381,7 @@ def main():
             t = torch.tensor([e2e_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_elapsed = float(t[0])
-        e2e = {"value": alg_bytes / e2e_elapsed / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * n * 8 * world,
+        e2e = {"value": alg_bytes / e2e_elapsed / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * n * 8,   # N>1: 1/world of the rows per rank over PCIe, the rest over NVLink
                "d2h_bytes_per_step": (n + 1) * 4 * world, "ms_per_step": 1e3 * e2e_elapsed / args.steps}
         if world == 1:
             fnn.release_cache()

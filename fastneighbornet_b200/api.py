@@ -61,6 +61,7 @@ ABI_SYMBOLS = [
     "fnn_ctx_trace", "fnn_ctx_stats", "fnn_ctx_matrix_ptr", "fnn_order", "fnn_rowsums", "fnn_seq_sum",
     "fnn_split_weights", "fnn_csw_matvec", "fnn_ctx_ipc_handle", "fnn_ctx_connect", "fnn_weighted_splits", "fnn_network",
     "fnn_phylip_taxa", "fnn_read_phylip", "fnn_write_nexus", "fnn_java_double_to_string", "fnn_release_cache",
+    "fnn_ctx_load_host_rows", "fnn_ctx_commit_load",
 ]
 
 
@@ -87,6 +88,8 @@ def lib():
         L.fnn_ctx_destroy.restype = None
         L.fnn_ctx_load_host.argtypes = [vp, c_dp]
         L.fnn_ctx_load_device.argtypes = [vp, vp, ctypes.c_int64]
+        L.fnn_ctx_load_host_rows.argtypes = [vp, c_dp, ctypes.c_int64, ctypes.c_int64]
+        L.fnn_ctx_commit_load.argtypes = [vp]
         L.fnn_ctx_synth.argtypes = [vp, c_dp, c_dp, ctypes.POINTER(ctypes.c_int64), ctypes.c_uint64, ctypes.c_double]
         L.fnn_ctx_read_matrix.argtypes = [vp, c_dp]
         L.fnn_ctx_order.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
@@ -185,6 +188,32 @@ class Context:
         D = np.ascontiguousarray(D, dtype=np.float64)
         assert D.shape == (self.n, self.n)
         _check(lib().fnn_ctx_load_host(self._h, _dp(D)))
+
+    def load_host_sharded(self, D):
+        """N>1 (torch.distributed initialised, contexts wired): every rank uploads 1/world of the rows over its own PCIe
+        link, the row blocks then travel between the GPUs over NVLink (NCCL broadcast on the library's device matrix) -
+        n*n*8 bytes cross PCIe in total instead of n*n*8 per rank."""
+        import torch
+        import torch.distributed as dist
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        assert D.shape == (self.n, self.n)
+        world, rank = dist.get_world_size(), dist.get_rank()
+        bounds = [self.n * r // world for r in range(world + 1)]
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        _check(lib().fnn_ctx_load_host_rows(self._h, _dp(D[r0:r1]), r0, r1 - r0))
+        dptr, ld = self.matrix_ptr()
+
+        class _View:
+            def __init__(s_, ptr, shape):
+                s_.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+        dev = torch.device("cuda", int(self.opts.device))
+        view = torch.as_tensor(_View(dptr, (self.n, ld)), device=dev)
+        for r in range(world):
+            if bounds[r + 1] > bounds[r]:
+                dist.broadcast(view[bounds[r]:bounds[r + 1]], src=r)
+        torch.cuda.synchronize(dev)
+        _check(lib().fnn_ctx_commit_load(self._h))
 
     def load_device(self, dptr, ld):
         _check(lib().fnn_ctx_load_device(self._h, ctypes.c_void_p(int(dptr)), int(ld)))

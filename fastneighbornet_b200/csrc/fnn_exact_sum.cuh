@@ -155,7 +155,10 @@ __device__ void block_exact_seq_sum(SmemT* sm, int len, Loader load, Present pre
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const double x = a[r][q] * scale[r];
-                    const double R = rint(x);
+                    // round-to-nearest-even to an integer without FRND.F64: exact for 0 <= x < 2^52 under the default
+                    // rounding mode (no FMA contraction, no fast-math), and x >= 2^52 is already an integer; x < 0 marks
+                    // the segment invalid below, whatever R is
+                    const double R = (x < 4503599627370496.0) ? (x + 4503599627370496.0) - 4503599627370496.0 : x;
                     bad[r] |= (a[r][q] < 0.0) | (fabs(x - R) == 0.5);
                     anynz[r] |= (a[r][q] != 0.0);
                     C[r] += R;
@@ -186,7 +189,7 @@ __device__ void block_exact_seq_sum(SmemT* sm, int len, Loader load, Present pre
     }
     __syncthreads();
 #ifdef FNN_XSUM_TIMING
-    long long t2_ = clock64();
+    long long t2_ = clock64(), tp_ = 0;
     int ncoop_ = 0, nleaf_ = 0;
 #endif
     // ---- B: warp r walks chain r
@@ -232,8 +235,7 @@ __device__ void block_exact_seq_sum(SmemT* sm, int len, Loader load, Present pre
             const int S0 = min(32, (PROLOGUE + L - 1) / L);
             leaf_sum(0, min(S0 * L, len));
 #ifdef FNN_XSUM_TIMING
-            const long long tp_ = clock64();
-            if (lane == 0) printf("chain %d: prologue %lld cycles\n", r, tp_ - t2_);
+            tp_ = clock64();
 #endif
             open_warp(0, S0);
             int s2 = 1;
@@ -249,7 +251,7 @@ __device__ void block_exact_seq_sum(SmemT* sm, int len, Loader load, Present pre
         }
         if (lane == 0) sm->result[r] = s;
 #ifdef FNN_XSUM_TIMING
-        if (lane == 0) printf("chain %d: A1=%lld A2=%lld walk=%lld cycles, coop steps=%d leaf elements=%d L=%d\n", r, t1_ - t0_, t2_ - t1_, clock64() - t2_, ncoop_, nleaf_, L);
+        if (lane == 0) printf("chain %d: A1=%lld A2=%lld prologue=%lld walk(after prologue)=%lld cycles, coop steps=%d leaf elements=%d L=%d\n", r, t1_ - t0_, t2_ - t1_, tp_ - t2_, clock64() - tp_, ncoop_, nleaf_, L);
 #endif
     }
     __syncthreads();

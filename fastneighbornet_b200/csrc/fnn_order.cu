@@ -1131,6 +1131,26 @@ extern "C" int fnn_ctx_load_host(fnn_ctx* c, const double* Dh) {
     return rc;
 }
 
+// Multi-GPU upload without replicating the PCIe traffic: every rank uploads only rows [row0, row0 + nrows) of the host
+// matrix; the host layer then moves the blocks between the ranks over NVLink (torch.distributed broadcast on
+// fnn_ctx_matrix_ptr) and calls fnn_ctx_commit_load.
+extern "C" int fnn_ctx_load_host_rows(fnn_ctx* c, const double* Dh_rows, int64_t row0, int64_t nrows) {
+    if (!c || !Dh_rows || row0 < 0 || nrows < 0 || row0 + nrows > c->n) { fnn::set_error("fnn_ctx_load_host_rows: bad argument"); return FNN_E_ARG; }
+    FNN_CUDA(cudaSetDevice(c->o.device));
+    if (nrows > 0)
+        FNN_CUDA(cudaMemcpy2DAsync(c->D + row0 * c->ld, c->ld * sizeof(double), Dh_rows, c->n * sizeof(double), c->n * sizeof(double), nrows,
+                                   cudaMemcpyHostToDevice, c->stream));
+    FNN_CUDA(cudaStreamSynchronize(c->stream));
+    return FNN_OK;
+}
+extern "C" int fnn_ctx_commit_load(fnn_ctx* c) {
+    if (!c) { fnn::set_error("fnn_ctx_commit_load: null argument"); return FNN_E_ARG; }
+    FNN_CUDA(cudaSetDevice(c->o.device));
+    int rc = after_load(c);
+    FNN_CUDA(cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
 extern "C" int fnn_ctx_load_device(fnn_ctx* c, const double* dD, int64_t ld_src) {
     if (!c || !dD || ld_src < c->n) { fnn::set_error("fnn_ctx_load_device: bad argument"); return FNN_E_ARG; }
     FNN_CUDA(cudaSetDevice(c->o.device));

@@ -91,6 +91,11 @@ int fnn_ctx_create(const fnn_opts* o, int64_t n, fnn_ctx** out);
 void fnn_ctx_destroy(fnn_ctx* c);
 /* upload an n*n row-major symmetric zero-diagonal host matrix (the Java double[][] D of FastNN.java:307-312) */
 int fnn_ctx_load_host(fnn_ctx* c, const double* D_rowmajor);
+/* multi-GPU upload without replicating the PCIe traffic: upload only rows [row0, row0+nrows) (nrows*n doubles, row-major);
+ * the host layer moves the row blocks between the ranks over NVLink (e.g. torch.distributed.broadcast on the matrix of
+ * fnn_ctx_matrix_ptr), then fnn_ctx_commit_load marks the matrix loaded (zero diagonal enforced) */
+int fnn_ctx_load_host_rows(fnn_ctx* c, const double* D_rows, int64_t row0, int64_t nrows);
+int fnn_ctx_commit_load(fnn_ctx* c);
 /* copy from a device matrix with leading dimension ld_src (elements) */
 int fnn_ctx_load_device(fnn_ctx* c, const double* dD, int64_t ld_src);
 /* synthesise the SURVEY §8(d) additive-tree + noise matrix in device memory from O(n) host parameters

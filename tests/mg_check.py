@@ -20,8 +20,8 @@ for name, D in cases:
         c.connect_torch()
         c.load_host(D)
         o = c.order(); tr = c.trace()
-        # second run on the same wired context (mailbox tags must not collide)
-        c.load_host(D)
+        # second run on the same wired context (mailbox tags must not collide), uploaded 1/world per rank + NVLink broadcast
+        c.load_host_sharded(D)
         o2 = c.order()
     with fnn.Context(n, device=lr, record_trace=1) as c1:   # un-wired single-GPU run on the same device
         c1.load_host(D)
