@@ -8,6 +8,7 @@
 // registers or occupancy.  Included by fnn_order.cu (needs DevState, Partial, better()).
 #pragma once
 #include <cuda.h>
+#include "fnn_tile_iter.h"
 
 namespace tma {
 
@@ -18,11 +19,9 @@ constexpr int THREADS = CONSUMERS + 32;     // + 1 producer warp
 constexpr int BOX_W = 256;                  // TMA box: 256 columns (2 KB) ...
 constexpr int BOX_R = 8;                    // ... x 8 rows
 constexpr int RPG = BOX_R / NGROUPS;        // rows per consumer group per chunk (even)
-constexpr int TILE_COLS = 2 * BOX_W;        // 512 columns = 2 boxes per stage
-constexpr int TILE_ROWS = 32;               // rows per tile = 4 chunks
+static_assert(TILE_COLS == 2 * BOX_W && TILE_ROWS == 4 * BOX_R, "tile = 2 boxes wide, 4 chunks high");
 constexpr int STAGES = 6;
 constexpr int STAGE_BYTES = 2 * BOX_R * BOX_W * 8;   // 32 KB
-constexpr int KPB = TILE_COLS / TILE_ROWS;  // row tiles per 512-row band
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,26 +54,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
 }
-
-struct TileIter {   // identical tile sequence for producer and consumers
-    long long t, total;
-    int stride;
-    __device__ TileIter(int m, int first, int stride_) : t(first), stride(stride_) {
-        const int nRowTiles = (m + TILE_ROWS - 1) / TILE_ROWS;
-        const int gFull = nRowTiles / KPB, rRem = nRowTiles % KPB;
-        total = (long long)KPB * gFull * (gFull + 1) / 2 + (long long)rRem * (gFull + 1);
-    }
-    __device__ bool valid() const { return t < total; }
-    __device__ void next() { t += stride; }
-    __device__ void decode(int& r0, int& cb0) const {
-        long long g = (long long)((sqrt(8.0 * (double)t / KPB + 1.0) - 1.0) * 0.5);
-        while ((long long)KPB * g * (g + 1) / 2 > t) --g;
-        while ((long long)KPB * (g + 1) * (g + 2) / 2 <= t) ++g;
-        const long long rem = t - (long long)KPB * g * (g + 1) / 2;
-        r0 = ((int)g * KPB + (int)(rem / (g + 1))) * TILE_ROWS;
-        cb0 = (int)(rem % (g + 1)) * TILE_COLS;
-    }
-};
 
 struct __align__(16) RowData { double S; long long pos; };   // one LDS.128 per row
 

@@ -26,6 +26,7 @@ def lib():
         so = os.path.join(_HERE, "liboracle.so")
         srcs = [os.path.join(_HERE, f) for f in ("nnet_oracle.cpp", "csw_l1.cpp")]
         srcs.append(os.path.join(os.path.dirname(_HERE), "fastneighbornet_b200", "csrc", "fnn_relaxed_sm.h"))
+        srcs.append(os.path.join(os.path.dirname(_HERE), "fastneighbornet_b200", "csrc", "fnn_tile_iter.h"))
         if not os.path.exists(so) or any(os.path.exists(s_) and os.path.getmtime(s_) > os.path.getmtime(so) for s_ in srcs):
             build()
         L = ctypes.CDLL(so)
@@ -48,6 +49,8 @@ def lib():
         L.oracle_l1_split_weights.argtypes = [ctypes.c_int64, c_dp, c_dp, c_lp]
         L.oracle_set_relaxed_sm.argtypes = [ctypes.c_int]
         L.oracle_java_random.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_ip]
+        L.oracle_tile_sequence.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_ip, c_ip, ctypes.c_int64]
+        L.oracle_tile_sequence.restype = ctypes.c_int64
         _LIB = L
     return _LIB
 
@@ -130,6 +133,20 @@ def java_random(seed, bound, count):
     out = np.zeros(count, dtype=np.int32)
     lib().oracle_java_random(seed, bound, count, _ip(out))
     return out
+
+
+def tile_sequence(m, rank, world, cta, grid):
+    """The tiles CTA `cta` (of `grid` per rank) of rank `rank` (of `world`) scans for m active nodes, from the PRODUCT's
+    TileIter (csrc/fnn_tile_iter.h) compiled for the host: list of (first row, first column)."""
+    need = lib().oracle_tile_sequence(m, rank, world, cta, grid, None, None, 0)
+    r0 = np.zeros(max(1, need), dtype=np.int32)
+    c0 = np.zeros(max(1, need), dtype=np.int32)
+    lib().oracle_tile_sequence(m, rank, world, cta, grid, _ip(r0), _ip(c0), need)
+    return [(int(a), int(b)) for a, b in zip(r0[:need], c0[:need])]
+
+
+def tile_shape():
+    return lib().oracle_tile_rows(), lib().oracle_tile_cols()
 
 
 def l1_ab(n, b):

@@ -36,6 +36,7 @@
 // the PRODUCT's resumable state machine for the Relaxed control flow, compiled here for the CPU so that it can be
 // held against the literal findNodes below (tests/test_relaxed_sm_cpu.py); the oracle never depends on it otherwise
 #include "../fastneighbornet_b200/csrc/fnn_relaxed_sm.h"
+#include "../fastneighbornet_b200/csrc/fnn_tile_iter.h"
 
 namespace {
 static int g_use_relaxed_sm = 0;
@@ -1033,6 +1034,22 @@ int oracle_split_weights(int64_t n, const double* d_pos, double* x, int constrai
 }
 
 // java.util.Random stream, for pinning the LCG against published known answers
+// The PRODUCT's tile sequence / multi-GPU partition (csrc/fnn_tile_iter.h), compiled for the host so that the CPU (gloo)
+// tests of the N>1 path exercise the kernels' own code, not a mirror: tiles of CTA `cta` of rank `rank` (world ranks,
+// `grid` CTAs per rank) for m active nodes -> (first row, first column) pairs; returns the count (or the count needed).
+int64_t oracle_tile_sequence(int m, int rank, int world, int cta, int grid, int32_t* r0_out, int32_t* c0_out, int64_t cap) {
+    int64_t k = 0;
+    for (tma::TileIter it(m, rank + world * cta, world * grid); it.valid(); it.next()) {
+        int r0, c0;
+        it.decode(r0, c0);
+        if (k < cap) { r0_out[k] = r0; c0_out[k] = c0; }
+        ++k;
+    }
+    return k;
+}
+int oracle_tile_rows(void) { return tma::TILE_ROWS; }
+int oracle_tile_cols(void) { return tma::TILE_COLS; }
+
 void oracle_java_random(int64_t seed, int32_t bound, int32_t count, int32_t* out) {
     JavaRandom r(seed);
     for (int i = 0; i < count; ++i) out[i] = r.nextInt(bound);

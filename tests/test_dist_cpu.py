@@ -1,5 +1,6 @@
-"""CPU, world_size 2, gloo: the host-side logic of the N>1 path - tile partition of the sharded scan and the
-min-loc merge rule - exercised through a real torch.distributed rendezvous (no GPU, no compute calls)."""
+"""CPU, world_size 2, gloo: the N>1 path's tile partition - the PRODUCT's TileIter (csrc/fnn_tile_iter.h, compiled for the
+host in the oracle library) with the kernels' (rank, CTA, grid) start/stride - and the min-loc merge rule, exercised
+through a real torch.distributed rendezvous (no GPU, no compute calls)."""
 import os
 import socket
 import sys
@@ -18,8 +19,12 @@ def _free_port():
 
 def _worker(rank, world, port, m, out):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
-    from fastneighbornet_b200 import sharding
+    import oracle
+    import sharding_model as sharding
+    TILE_ROWS, TILE_COLS = oracle.tile_shape()
+    GRID = 5   # CTAs per rank (the kernels use the SM count; any grid must partition the same way)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -28,11 +33,10 @@ def _worker(rank, world, port, m, out):
     A = rng.integers(0, 5, size=(m, m)).astype(np.float64)   # ties on purpose
     Q = np.tril(A + A.T, -1)
     mine = None
-    tiles = list(sharding.rank_tiles(m, rank, world))
-    for t in tiles:
-        r0, c0 = sharding.decode_tile(t)
-        for i in range(r0, min(r0 + sharding.TILE_ROWS, m)):
-            for j in range(c0, min(c0 + sharding.TILE_COLS, i)):
+    tiles = [t for cta in range(GRID) for t in oracle.tile_sequence(m, rank, world, cta, GRID)]
+    for r0, c0 in tiles:
+        for i in range(r0, min(r0 + TILE_ROWS, m)):
+            for j in range(c0, min(c0 + TILE_COLS, i)):
                 mine = sharding.merge_partials([mine, (Q[i, j], i, j)] if mine else [(Q[i, j], i, j)])
     gathered = [None] * world
     dist.all_gather_object(gathered, (mine, tiles))
@@ -44,7 +48,8 @@ def _worker(rank, world, port, m, out):
         for j in range(i):
             if ref is None or Q[i, j] < ref[0]:
                 ref = (Q[i, j], i, j)
-    out.put((rank, winner == ref, all_tiles == list(range(sharding.total_tiles(m)))))
+    single = sorted(t for cta in range(GRID) for t in oracle.tile_sequence(m, 0, 1, cta, GRID))   # world = 1: every tile
+    out.put((rank, winner == ref, all_tiles == single and len(set(all_tiles)) == len(all_tiles)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,13 +69,18 @@ def test_sharded_scan_partition_and_merge_gloo():
     assert all(ok_w and ok_t for _, ok_w, ok_t in res), res
 
 
-def test_tile_decode_covers_triangle():
+def test_tile_sequence_covers_triangle_exactly_once():
+    """The product's TileIter: for any (world, grid) the tiles of all ranks and CTAs cover every entry below the diagonal
+    exactly once (so the sharded scan reads the algorithmic bytes and no pair is evaluated twice or skipped)."""
     sys.path.insert(0, ROOT)
-    from fastneighbornet_b200 import sharding
-    for m in (5, 33, 512, 513, 1500):
-        seen = np.zeros((m, m), dtype=np.int32)
-        for t in range(sharding.total_tiles(m)):
-            r0, c0 = sharding.decode_tile(t)
-            for i in range(r0, min(r0 + sharding.TILE_ROWS, m)):
-                seen[i, c0:min(c0 + sharding.TILE_COLS, i)] += 1
-        assert (np.tril(seen, -1) == np.tril(np.ones((m, m), dtype=np.int32), -1)).all()
+    import oracle
+    TR, TC = oracle.tile_shape()
+    for m in (5, 33, 512, 513, 1500, 4099):
+        for world, grid in ((1, 3), (2, 5), (8, 7)):
+            seen = np.zeros((m, m), dtype=np.int32)
+            for rank in range(world):
+                for cta in range(grid):
+                    for r0, c0 in oracle.tile_sequence(m, rank, world, cta, grid):
+                        for i in range(r0, min(r0 + TR, m)):
+                            seen[i, c0:min(c0 + TC, i)] += 1
+            assert (np.tril(seen, -1) == np.tril(np.ones((m, m), dtype=np.int32), -1)).all(), (m, world, grid)
