@@ -15,7 +15,6 @@
 // bit-identical to it; the distance to the reference's own summation order (L0) is the
 // algorithm's intrinsic noise floor and is reported by the tests.
 #include <cuda_runtime.h>
-#include <cub/cub.cuh>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -326,20 +325,164 @@ __global__ void __launch_bounds__(256) k_xr_update(double* __restrict__ x, doubl
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
-// ---------------------------------------------------------------- active-set helpers
-struct IsNeg { __device__ bool operator()(const double& v) const { return v < 0.0; } };
+// ---------------------------------------------------------------- active-set helpers (hand-written: no library calls)
+// State of the selection primitives, one per solver, in device memory.
+struct SelState {
+    unsigned long long prefix;    // radix select: digits of the k-th smallest key fixed so far
+    long long k;                  // rank still to be located inside the current bucket (0-based)
+    long long less;               // negatives strictly below the cutoff
+    long long num_neg, nkept, ties, slots;
+    double cutoff;
+    unsigned int ticket, pad;
+    unsigned int hist[256];
+    long long flag_total;         // flag scan: number of set flags
+    double ml_v; long long ml_i;  // min-loc result
+};
+constexpr int SEL_THREADS = 256;
 
-// (:314-328) x < cutoff -> contract; x == cutoff -> the earliest ties fill the remaining slots
-__global__ void k_mark_below(double* x, unsigned char* active, int64_t len, double cutoff, int* tie_flag) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
-        const double v = x[i];
-        tie_flag[i] = (v == cutoff) ? 1 : 0;
-        if (v < cutoff) { x[i] = 0.0; active[i] = 1; }
+// worstIndices (:282-330), step 1: count the negatives; the last block derives nkept = ceil(propKept * numNeg) (:309)
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_count_neg(const double* __restrict__ x, int64_t len, SelState* sel) {
+    __shared__ long long wsum[SEL_THREADS / 32];
+    long long cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) cnt += x[i] < 0.0;
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < SEL_THREADS / 32; ++w) t += wsum[w];
+        if (t) atomicAdd((unsigned long long*)&sel->num_neg, (unsigned long long)t);
+        __threadfence();
+        if (atomicAdd(&sel->ticket, 1u) == gridDim.x - 1) {
+            __threadfence();
+            const long long nn = *(volatile long long*)&sel->num_neg;
+            const long long nkept = (long long)ceil(0.6 * (double)nn);
+            sel->nkept = nkept; sel->k = nkept - 1; sel->prefix = 0; sel->less = 0; sel->ties = 0; sel->slots = 0;
+            sel->ticket = 0;
+        }
     }
 }
-__global__ void k_mark_ties(double* x, unsigned char* active, int64_t len, const int* tie_flag, const int* tie_rank, int64_t slots) {
+// step 2: the cutoff = the nkept-th smallest negative (:310), by an exact 8 x 8-bit radix select instead of a full sort.
+// For negative doubles, ascending value = ascending ~bits.  Pass p histograms digit p (from the top) of the keys that
+// agree with the digits fixed so far; the last block picks the bucket holding rank k.
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_radix_pass(const double* __restrict__ x, int64_t len, SelState* sel, int pass) {
+    if (sel->num_neg == 0) return;
+    __shared__ unsigned int h[256];
+    h[threadIdx.x] = 0;   // SEL_THREADS == 256
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    const unsigned long long prefix = sel->prefix;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        if (v < 0.0) {
+            const unsigned long long key = ~(unsigned long long)__double_as_longlong(v);
+            if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&h[(key >> shift) & 255], 1u);
+        }
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&sel->hist[threadIdx.x], h[threadIdx.x]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&sel->ticket, 1u) == gridDim.x - 1) {
+        __threadfence();
+        volatile unsigned int* gh = sel->hist;
+        long long k = sel->k, less = sel->less;
+        int b = 0;
+        for (; b < 255; ++b) {
+            const long long cb = gh[b];
+            if (k < cb) break;
+            k -= cb; less += cb;
+        }
+        sel->prefix = prefix | ((unsigned long long)b << shift);
+        sel->k = k; sel->less = less;
+        if (pass == 7) {
+            sel->ties = gh[b];                                         // entries equal to the cutoff
+            sel->cutoff = __longlong_as_double((long long)~sel->prefix);
+            sel->slots = sel->nkept - less;                            // result slots left for ties (filled from the back, :321-327)
+        }
+        for (int q = 0; q < 256; ++q) gh[q] = 0;
+        sel->ticket = 0;
+    }
+}
+// step 3 (:314-328 + the contraction :422-431): x < cutoff -> contract; x == cutoff -> the EARLIEST ties fill the remaining
+// slots.  When every tie fits (the common case: the cutoff value is unique) they are contracted here; otherwise they are
+// flagged and ranked by the flag scan below.
+__global__ void k_sel_mark(double* x, unsigned char* active, int64_t len, const SelState* sel, int* tie_flag) {
+    if (sel->num_neg == 0) return;
+    const double cutoff = sel->cutoff;
+    const bool rank_ties = sel->ties > sel->slots;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        int f = 0;
+        if (v < cutoff) { x[i] = 0.0; active[i] = 1; }
+        else if (v == cutoff) {
+            if (rank_ties) f = 1;
+            else { x[i] = 0.0; active[i] = 1; }
+        }
+        tie_flag[i] = f;
+    }
+}
+__global__ void k_sel_mark_ties(double* x, unsigned char* active, int64_t len, const SelState* sel, const int* tie_flag, const int* local_rank,
+                                const long long* block_excl) {
+    if (sel->num_neg == 0 || sel->ties <= sel->slots) return;
+    const long long slots = sel->slots;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
-        if (tie_flag[i] && tie_rank[i] < slots) { x[i] = 0.0; active[i] = 1; }
+        if (tie_flag[i] && block_excl[i >> 10] + local_rank[i] < slots) { x[i] = 0.0; active[i] = 1; }
+}
+
+// ---- exclusive prefix count of 0/1 flags in index order: rank(i) = block_excl[i / 1024] + local_rank[i]
+__global__ void __launch_bounds__(1024) k_flag_local(const int* __restrict__ flag, int64_t len, int* __restrict__ local_rank,
+                                                     long long* __restrict__ block_sum, const SelState* gate_ties) {
+    if (gate_ties && (gate_ties->num_neg == 0 || gate_ties->ties <= gate_ties->slots)) return;
+    __shared__ int wtot[32];
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = (i < len) ? flag[i] : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f != 0);
+    const int within = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) wtot[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        int v = wtot[lane];
+        const int own = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += t; }
+        wtot[lane] = v - own;
+        if (lane == 31) block_sum[blockIdx.x] = v;
+    }
+    __syncthreads();
+    if (i < len) local_rank[i] = wtot[warp] + within;
+}
+__global__ void __launch_bounds__(1024) k_flag_blockscan(long long* block_sum, int64_t nblk, SelState* sel, const SelState* gate_ties) {
+    if (gate_ties && (gate_ties->num_neg == 0 || gate_ties->ties <= gate_ties->slots)) return;
+    __shared__ long long wtot[32];
+    __shared__ long long carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < nblk; b0 += 1024) {
+        const int64_t b = b0 + threadIdx.x;
+        long long v = (b < nblk) ? block_sum[b] : 0;
+        const long long own = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += t; }
+        if (lane == 31) wtot[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = wtot[lane];
+            const long long wown = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += t; }
+            wtot[lane] = w - wown;
+        }
+        __syncthreads();
+        const long long carry = carry_s;
+        if (b < nblk) block_sum[b] = carry + wtot[warp] + (v - own);   // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + wtot[31] + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sel->flag_total = carry_s;
 }
 
 struct MinLoc { double v; long long i; };
@@ -370,6 +513,54 @@ struct GradIn {
     const double* r; const unsigned char* active;
     __device__ MinLoc operator()(long long i) const { return active[i] ? MinLoc{r[i], i} : MinLoc{0.0, -1}; }
 };
+// first strict minimum in index order over op(i), i < len (:438-448, :475-492, :369-374): grid-stride partials, then the last
+// block to finish reduces them (MinLocOp is associative and commutative, so the result does not depend on the schedule)
+template <typename InOp>
+__global__ void __launch_bounds__(SEL_THREADS) k_minloc(InOp op, int64_t len, MinLoc* partials, SelState* sel) {
+    __shared__ MinLoc wb[SEL_THREADS / 32];
+    __shared__ bool amLast;
+    MinLocOp red;
+    MinLoc best{0.0, -1};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) best = red(best, op(i));
+    auto warp_reduce = [&](MinLoc v) {
+        for (int off = 16; off > 0; off >>= 1) {
+            MinLoc o;
+            o.v = __shfl_xor_sync(0xffffffffu, v.v, off);
+            o.i = __shfl_xor_sync(0xffffffffu, v.i, off);
+            v = red(v, o);
+        }
+        return v;
+    };
+    best = warp_reduce(best);
+    if ((threadIdx.x & 31) == 0) wb[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < SEL_THREADS / 32; ++w) best = red(best, wb[w]);
+        partials[blockIdx.x] = best;
+        __threadfence();
+        amLast = (atomicAdd(&sel->ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (amLast) {
+        __threadfence();
+        MinLoc v{0.0, -1};
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += SEL_THREADS) {
+            MinLoc pb;
+            pb.v = __ldcg(&partials[b].v); pb.i = __ldcg(&partials[b].i);
+            v = red(v, pb);
+        }
+        v = warp_reduce(v);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) wb[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < SEL_THREADS / 32; ++w) v = red(v, wb[w]);
+            sel->ml_v = v.v; sel->ml_i = v.i;
+            sel->ticket = 0;
+        }
+    }
+}
+
 // (:452-455) old_x += min_xi * (x - old_x) on the free set
 __global__ void k_oldx_step(double* old_x, const double* x, const unsigned char* active, int64_t len, double min_xi) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
@@ -993,16 +1184,13 @@ struct Csw {
     unsigned long long* bar = nullptr;
     unsigned long long* prof = nullptr;   // FNN_CSW_PROF: per-phase ns of k_cg_persistent (CTA 0)
     int literal = 0;           // opts.reserved[4] == 2: the reference's own operation order (namespace lit), n <= 512
-    // cub scratch and the 60 % collapse work arrays
-    void* tmp = nullptr;
-    size_t tmp_bytes = 0;
-    double *neg = nullptr, *neg_sorted = nullptr;
-    int *d_count = nullptr, *tie_flag = nullptr, *tie_rank = nullptr;
-    void* d_minloc = nullptr;
-    int ensure_tmp(size_t need) {
-        if (need > tmp_bytes) { if (tmp) cudaFree(tmp); tmp = nullptr; FNN_CUDA(cudaMalloc(&tmp, need)); tmp_bytes = need; }
-        return FNN_OK;
-    }
+    // work arrays of the hand-written selection primitives (60 % collapse, argmins, split emission)
+    SelState* sel = nullptr;
+    SelState* h_sel = nullptr;          // pinned copy
+    MinLoc* ml_part = nullptr;          // per-block partial min-locs
+    int *tie_flag = nullptr, *tie_rank = nullptr;
+    long long* blk_sum = nullptr;       // flag scan: per-1024-block counts -> exclusive offsets
+    int sel_grid = 0;
 
     int* done_ptr() { return &sc->done; }
 
@@ -1017,8 +1205,11 @@ struct Csw {
         CSW_ALLOC(bar, 2);
         if (getenv("FNN_CSW_PROF")) { CSW_ALLOC(prof, 24); FNN_CUDA(cudaMemset(prof, 0, 24 * sizeof(unsigned long long))); }
         CSW_ALLOC(active, np); CSW_ALLOC(sc, 1);
-        CSW_ALLOC(neg, np); CSW_ALLOC(neg_sorted, np); CSW_ALLOC(tie_flag, np); CSW_ALLOC(tie_rank, np); CSW_ALLOC(d_count, 1);
-        FNN_CUDA(cudaMalloc(&d_minloc, 16));
+        sel_grid = (int)std::max<int64_t>(1, std::min<int64_t>((np + SEL_THREADS * 8 - 1) / (SEL_THREADS * 8), 148 * 4));
+        CSW_ALLOC(tie_flag, np); CSW_ALLOC(tie_rank, np); CSW_ALLOC(blk_sum, nblk + 1);
+        CSW_ALLOC(sel, 1); CSW_ALLOC(ml_part, sel_grid);
+        FNN_CUDA(cudaMemset(sel, 0, sizeof(SelState)));
+        FNN_CUDA(cudaMallocHost((void**)&h_sel, sizeof(SelState)));
         FNN_CUDA(cudaMallocHost((void**)&h_sc, sizeof(Scalars)));
         FNN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         FNN_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
@@ -1029,7 +1220,8 @@ struct Csw {
         cudaFree(d); cudaFree(x); cudaFree(r); cudaFree(w); cudaFree(p); cudaFree(y); cudaFree(old_x); cudaFree(AtWd);
         cudaFree(T); cudaFree(T2); cudaFree(Rw); cudaFree(P); cudaFree(RT); cudaFree(CT); cudaFree(PRS); cudaFree(part1); cudaFree(part2);
         cudaFree(active); cudaFree(sc); cudaFree(bar); cudaFree(prof);
-        cudaFree(neg); cudaFree(neg_sorted); cudaFree(tie_flag); cudaFree(tie_rank); cudaFree(d_count); cudaFree(d_minloc); cudaFree(tmp);
+        cudaFree(tie_flag); cudaFree(tie_rank); cudaFree(blk_sum); cudaFree(sel); cudaFree(ml_part);
+        if (h_sel) cudaFreeHost(h_sel);
         if (h_sc) cudaFreeHost(h_sc);
         if (st) cudaStreamDestroy(st);
     }
@@ -1145,69 +1337,29 @@ struct Csw {
 
 template <typename InOp>
 static int minloc_reduce(Csw& c, InOp op, MinLoc* out_host) {
-    MinLoc* d_out = reinterpret_cast<MinLoc*>(c.d_minloc);
-    cub::CountingInputIterator<long long> cnt(0);
-    cub::TransformInputIterator<MinLoc, InOp, cub::CountingInputIterator<long long>> it(cnt, op);
-    size_t need = 0;
-    FNN_CUDA(cub::DeviceReduce::Reduce(nullptr, need, it, d_out, (int)c.np, MinLocOp(), MinLoc{0.0, -1}, c.st));
-    if (c.ensure_tmp(need)) return FNN_E_CUDA;
-    FNN_CUDA(cub::DeviceReduce::Reduce(c.tmp, need, it, d_out, (int)c.np, MinLocOp(), MinLoc{0.0, -1}, c.st));
-    FNN_CUDA(cudaMemcpyAsync(out_host, d_out, sizeof(MinLoc), cudaMemcpyDeviceToHost, c.st));
+    k_minloc<InOp><<<c.sel_grid, SEL_THREADS, 0, c.st>>>(op, c.np, c.ml_part, c.sel);
+    c.launches += 1;
+    FNN_CUDA(cudaMemcpyAsync(c.h_sel, c.sel, sizeof(SelState), cudaMemcpyDeviceToHost, c.st));
     FNN_CUDA(cudaStreamSynchronize(c.st));
+    out_host->v = c.h_sel->ml_v; out_host->i = c.h_sel->ml_i;
     return FNN_OK;
 }
 
-// worstIndices(x, 0.6) + contraction (:282-330, :420-431); returns whether anything was contracted
+// worstIndices(x, 0.6) + contraction (:282-330, :420-431); returns whether anything was contracted.  Entirely on the device
+// (count, exact radix select of the cutoff, marking, tie ranking by a flag scan); the host reads one counter at the end.
 static int contract_worst(Csw& c, bool* contracted) {
-    double *neg = c.neg, *neg_sorted = c.neg_sorted;
-    int *d_count = c.d_count, *tie_flag = c.tie_flag, *tie_rank = c.tie_rank;
-    auto ensure = [&](size_t need) -> int { return c.ensure_tmp(need); };
-    void*& tmp = c.tmp;
-    size_t need = 0;
-    FNN_CUDA(cub::DeviceSelect::If(nullptr, need, c.x, neg, d_count, (int)c.np, IsNeg(), c.st));
-    if (ensure(need)) return FNN_E_CUDA;
-    FNN_CUDA(cub::DeviceSelect::If(tmp, need, c.x, neg, d_count, (int)c.np, IsNeg(), c.st));
-    int numNeg = 0;
-    FNN_CUDA(cudaMemcpyAsync(&numNeg, d_count, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+    FNN_CUDA(cudaMemsetAsync(&c.sel->num_neg, 0, sizeof(long long), c.st));
+    k_sel_count_neg<<<c.sel_grid, SEL_THREADS, 0, c.st>>>(c.x, c.np, c.sel);
+    for (int pass = 0; pass < 8; ++pass) k_sel_radix_pass<<<c.sel_grid, SEL_THREADS, 0, c.st>>>(c.x, c.np, c.sel, pass);
+    k_sel_mark<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.active, c.np, c.sel, c.tie_flag);
+    // more ties at the cutoff than slots left (rare): rank the ties in index order, the earliest fill the slots
+    k_flag_local<<<(unsigned)c.nblk, 1024, 0, c.st>>>(c.tie_flag, c.np, c.tie_rank, c.blk_sum, c.sel);
+    k_flag_blockscan<<<1, 1024, 0, c.st>>>(c.blk_sum, c.nblk, c.sel, c.sel);
+    k_sel_mark_ties<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.active, c.np, c.sel, c.tie_flag, c.tie_rank, c.blk_sum);
+    c.launches += 13;
+    FNN_CUDA(cudaMemcpyAsync(c.h_sel, c.sel, sizeof(SelState), cudaMemcpyDeviceToHost, c.st));
     FNN_CUDA(cudaStreamSynchronize(c.st));
-    *contracted = false;
-    if (numNeg == 0) return FNN_OK;
-    need = 0;
-    FNN_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, neg, neg_sorted, numNeg, 0, 64, c.st));
-    if (ensure(need)) return FNN_E_CUDA;
-    FNN_CUDA(cub::DeviceRadixSort::SortKeys(tmp, need, neg, neg_sorted, numNeg, 0, 64, c.st));
-    const int64_t nkept = (int64_t)std::ceil(0.6 * (double)numNeg);
-    double cutoff = 0.0;
-    FNN_CUDA(cudaMemcpyAsync(&cutoff, neg_sorted + (nkept - 1), sizeof(double), cudaMemcpyDeviceToHost, c.st));
-    // number strictly below the cutoff = first index of cutoff in the sorted negatives (binary search on host copy is
-    // avoided: count with the tie scan below)
-    FNN_CUDA(cudaStreamSynchronize(c.st));
-    k_mark_below<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.active, c.np, cutoff, tie_flag);
-    // strictly-less count: lower_bound in neg_sorted
-    need = 0;
-    FNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, tie_flag, tie_rank, (int)c.np, c.st));
-    if (ensure(need)) return FNN_E_CUDA;
-    FNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, need, tie_flag, tie_rank, (int)c.np, c.st));
-    // ties fill result[back--] while back >= front: slots = nkept - (#strictly less)
-    // #strictly less = numNeg_sorted lower_bound(cutoff): fetch by a tiny device binary search on the host side
-    int64_t lo = 0, hi = nkept - 1;   // neg_sorted[nkept-1] == cutoff, so the lower bound is in [0, nkept-1]
-    if (nkept >= 2) {   // common case: no tie at the cutoff
-        double prev;
-        FNN_CUDA(cudaMemcpyAsync(&prev, neg_sorted + (nkept - 2), sizeof(double), cudaMemcpyDeviceToHost, c.st));
-        FNN_CUDA(cudaStreamSynchronize(c.st));
-        if (prev < cutoff) lo = hi;
-    }
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) / 2;
-        double v;
-        FNN_CUDA(cudaMemcpyAsync(&v, neg_sorted + mid, sizeof(double), cudaMemcpyDeviceToHost, c.st));
-        FNN_CUDA(cudaStreamSynchronize(c.st));
-        if (v < cutoff) lo = mid + 1; else hi = mid;
-    }
-    const int64_t slots = nkept - lo;
-    k_mark_ties<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.active, c.np, tie_flag, tie_rank, slots);
-    c.launches += 6;
-    *contracted = true;
+    *contracted = c.h_sel->num_neg > 0;
     return FNN_OK;
 }
 
@@ -1361,37 +1513,43 @@ extern "C" int fnn_split_weights(const fnn_opts* o, const int32_t* ordering, con
     return rc;
 }
 
-// (:94-108 / FastNN.java:455-466) keep x > cutoff, in (i,j) row-major-upper order - compacted on the device so that only
-// the ~3.7 n surviving splits cross PCIe instead of n(n-1)/2 weights
+// (:94-108 / FastNN.java:455-466) keep x > cutoff, in (i,j) row-major-upper order - compacted on the device (flag scan of the
+// selection primitives above) so that only the ~3.7 n surviving splits cross PCIe instead of n(n-1)/2 weights
 __global__ void k_flag_above(const double* __restrict__ x, int* __restrict__ flag, int64_t len, double cutoff) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) flag[i] = x[i] > cutoff;
 }
-__global__ void k_gather(const double* __restrict__ x, const int* __restrict__ idx, double* __restrict__ out, int count) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = x[idx[i]];
+// compaction in index order: flagged entry i goes to slot block_excl[i / 1024] + local_rank[i]
+__global__ void k_compact(const double* __restrict__ x, const int* __restrict__ flag, const int* __restrict__ local_rank,
+                          const long long* __restrict__ block_excl, int64_t len, int* __restrict__ idx_out, double* __restrict__ w_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        if (flag[i]) {
+            const long long k = block_excl[i >> 10] + local_rank[i];
+            idx_out[k] = (int)i;
+            w_out[k] = x[i];
+        }
 }
 
 // FastNN.java:455-466 on the device: keep the splits whose weight exceeds `cutoff`, compacted in (i, j) order.
 static int emit_kept_splits(Csw& c, int64_t n, double cutoff, int32_t* split_i, int32_t* split_j, double* weight, int64_t max_out,
                             int64_t* n_out) {
     k_flag_above<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.tie_flag, c.np, cutoff);
-    cub::CountingInputIterator<int> idx(0);
-    size_t need = 0;
-    FNN_CUDA(cub::DeviceSelect::Flagged(nullptr, need, idx, c.tie_flag, c.tie_rank, c.d_count, (int)c.np, c.st));
-    if (c.ensure_tmp(need)) return FNN_E_CUDA;
-    FNN_CUDA(cub::DeviceSelect::Flagged(c.tmp, need, idx, c.tie_flag, c.tie_rank, c.d_count, (int)c.np, c.st));
-    int kept = 0;
-    FNN_CUDA(cudaMemcpyAsync(&kept, c.d_count, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+    k_flag_local<<<(unsigned)c.nblk, 1024, 0, c.st>>>(c.tie_flag, c.np, c.tie_rank, c.blk_sum, nullptr);
+    k_flag_blockscan<<<1, 1024, 0, c.st>>>(c.blk_sum, c.nblk, c.sel, nullptr);
+    FNN_CUDA(cudaMemcpyAsync(c.h_sel, c.sel, sizeof(SelState), cudaMemcpyDeviceToHost, c.st));
     FNN_CUDA(cudaStreamSynchronize(c.st));
+    const long long kept = c.h_sel->flag_total;
     *n_out = kept;
-    if (kept > max_out) { fnn::set_error("weighted splits: %d splits kept, room for %lld", kept, (long long)max_out); return FNN_E_ARG; }
+    if (kept > max_out) { fnn::set_error("weighted splits: %lld splits kept, room for %lld", kept, (long long)max_out); return FNN_E_ARG; }
     if (kept > 0) {
-        k_gather<<<c.grid1d(kept, 256), 256, 0, c.st>>>(c.x, c.tie_rank, c.neg, kept);
-        std::vector<int> idx_h(kept);
-        FNN_CUDA(cudaMemcpyAsync(idx_h.data(), c.tie_rank, sizeof(int) * kept, cudaMemcpyDeviceToHost, c.st));
-        FNN_CUDA(cudaMemcpyAsync(weight, c.neg, sizeof(double) * kept, cudaMemcpyDeviceToHost, c.st));
+        // the solver's scratch vectors are free now: p holds the kept weights, the first kept ints of w their packed indices
+        int* d_idx = reinterpret_cast<int*>(c.w);
+        k_compact<<<c.grid1d(c.np, 256), 256, 0, c.st>>>(c.x, c.tie_flag, c.tie_rank, c.blk_sum, c.np, d_idx, c.p);
+        std::vector<int> idx_h((size_t)kept);
+        FNN_CUDA(cudaMemcpyAsync(idx_h.data(), d_idx, sizeof(int) * (size_t)kept, cudaMemcpyDeviceToHost, c.st));
+        FNN_CUDA(cudaMemcpyAsync(weight, c.p, sizeof(double) * (size_t)kept, cudaMemcpyDeviceToHost, c.st));
         FNN_CUDA(cudaStreamSynchronize(c.st));
         int64_t i = 0;
-        for (int k = 0; k < kept; ++k) {   // packed index -> (i, j); indices are increasing, so i only moves forward
+        for (long long k = 0; k < kept; ++k) {   // packed index -> (i, j); indices are increasing, so i only moves forward
             while (row_start(n, i + 1) <= idx_h[k]) ++i;
             split_i[k] = (int32_t)i;
             split_j[k] = (int32_t)(idx_h[k] - row_start(n, i) + i + 1);
