@@ -687,18 +687,18 @@ __device__ double cgp_reduce(const double* part, long long nblk, double* lv, dou
     return v;
 }
 
-// blocks of 32 of one row: Kogge-Stone inside, carry added sequentially (k_rowscan); e is this lane's element
-__device__ __forceinline__ double scan32_carry(double e, double& carry, int lane) {
+// Kogge-Stone inclusive scan of one 32-block (no carry): the blocks of a row are independent up to here, so several of them
+// are scanned back to back (their shuffle chains overlap) before the short sequential carry chain
+//   out_b = carry_b + local_b,  carry_{b+1} = out_b[31]
+// is applied - the same operands in the same order as scanning block after block, hence the same bits.
+__device__ __forceinline__ double scan32_local(double e, int lane) {
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const double t = __shfl_up_sync(0xffffffffu, e, off);
         if (lane >= off) e = e + t;
     }
-    const double out = carry + e;
-    carry = __shfl_sync(0xffffffffu, out, 31);
-    return out;
+    return e;
 }
-
 // chunk-local column scan of COL_CHUNK rows from zero (k_colscan_local): all loads of a half-chunk first, then the chain
 template <bool WITH_CT>
 __device__ __forceinline__ void colscan_local_thread(const double* Rw, const double* v, double* P, double* T, double* T2, int n, int c,
@@ -815,16 +815,23 @@ __global__ void __launch_bounds__(CGP_THREADS, 1) k_cg_persistent(CgArgs a) {
                     rv[u] = 0.0; pv[u] = 0.0;
                     if (idx < len) { rv[u] = ldg_cg(a.r + rs + idx); if (!first) pv[u] = ldg_cg(a.p + rs + idx); }
                 }
+                double loc[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
+                for (int u = 0; u < U; ++u) {              // U independent block scans
+                    const int idx = b0 + 32 * u + lane;
+                    double e = 0.0;
+                    if (idx < len) {
+                        e = first ? rv[u] : rv[u] + beta * pv[u];
+                        a.p[rs + idx] = e;
+                    }
+                    loc[u] = scan32_local(e, lane);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {              // the carry chain
                     if (b0 + 32 * u < len) {
                         const int idx = b0 + 32 * u + lane;
-                        double e = 0.0;
-                        if (idx < len) {
-                            e = first ? rv[u] : rv[u] + beta * pv[u];
-                            a.p[rs + idx] = e;
-                        }
-                        const double out = scan32_carry(e, carry, lane);
+                        const double out = carry + loc[u];
+                        carry = __shfl_sync(0xffffffffu, out, 31);
                         if (idx < len) a.Rw[rs + idx] = out;
                     }
                 }
@@ -871,23 +878,30 @@ __global__ void __launch_bounds__(CGP_THREADS, 1) k_cg_persistent(CgArgs a) {
                         pl[u] = ldg_cg(a.P + prow + (b - 1));
                     }
                 }
+                double loc[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
+                for (int u = 0; u < U; ++u) {              // U independent block scans
+                    const int idx = b0 + 32 * u + lane;
+                    double e = 0.0;
+                    if (idx < len) {
+                        const int b = i + 1 + idx;
+                        const double P1 = (i >= 1) ? tc[u] + pl[u] : 0.0;
+                        double t = 2.0 * P1;
+                        t = t - Pda;
+                        t = t + vecB[b];
+                        t = t - Prowa;
+                        t = t - vecA[b];
+                        e = t;
+                        a.y[rs + idx] = t;
+                    }
+                    loc[u] = scan32_local(e, lane);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {              // the carry chain
                     if (b0 + 32 * u < len) {
                         const int idx = b0 + 32 * u + lane;
-                        double e = 0.0;
-                        if (idx < len) {
-                            const int b = i + 1 + idx;
-                            const double P1 = (i >= 1) ? tc[u] + pl[u] : 0.0;
-                            double t = 2.0 * P1;
-                            t = t - Pda;
-                            t = t + vecB[b];
-                            t = t - Prowa;
-                            t = t - vecA[b];
-                            e = t;
-                            a.y[rs + idx] = t;
-                        }
-                        const double out = scan32_carry(e, carry, lane);
+                        const double out = carry + loc[u];
+                        carry = __shfl_sync(0xffffffffu, out, 31);
                         if (idx < len) a.Rw[rs + idx] = out;
                     }
                 }
@@ -915,12 +929,22 @@ __global__ void __launch_bounds__(CGP_THREADS, 1) k_cg_persistent(CgArgs a) {
             vecB[j] = (j >= 1) ? fixed_P(a.P, a.T, n, j - 1, j) : 0.0;
         }
         __syncthreads();
-        if (tid < 32) {                                // ... then the blocked scan in place, from shared memory
+        // ... then the blocked scan in place, from shared memory: every warp scans 32-blocks locally, one warp applies the
+        // sequential carries (out_b = carry_b + local_b, carry_{b+1} = out_b[31]: k_prs's operands and order)
+        for (int blk = (tid >> 5) * 32; blk < n; blk += CGP_THREADS) {
+            const double e = (blk + lane < n) ? vecA[blk + lane] : 0.0;
+            const double l = scan32_local(e, lane);
+            if (blk + lane < n) vecA[blk + lane] = l;
+        }
+        __syncthreads();
+        if (tid < 32) {
             double carry = 0.0;
             for (int blk = 0; blk < n; blk += 32) {
-                const double e = (blk + lane < n) ? vecA[blk + lane] : 0.0;
-                const double out = scan32_carry(e, carry, lane);
+                const int last = min(blk + 31, n - 1);
+                const double out = (blk + lane < n) ? carry + vecA[blk + lane] : 0.0;
                 if (blk + lane < n) vecA[blk + lane] = out;
+                // the block's last lane in k_prs is lane 31 of a zero-padded block: its value equals the last valid entry's
+                carry = __shfl_sync(0xffffffffu, out, last - blk);
             }
         }
         __syncthreads();
