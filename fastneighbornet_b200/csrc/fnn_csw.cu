@@ -22,6 +22,7 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 #include "fastnn.h"
 #include "fnn_common.h"
 #include "fnn_exact_sum.cuh"
@@ -1203,6 +1204,7 @@ struct Csw {
     Scalars* h_sc = nullptr;
     cudaGraphExec_t cg_graph = nullptr;
     int64_t cg_calls = 0, outer = 0, inner = 0, launches = 0, launches_per_graph = 0;
+    std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
     int persistent = 0;        // 1: k_cg_persistent (one cooperative launch per CG solve) instead of the graph path
     int persistent_grid = 0;
     unsigned long long* bar = nullptr;
@@ -1326,10 +1328,21 @@ struct Csw {
             long long per_launch = 1 << 16;
             if (const char* e = getenv("FNN_CSW_ITERS_PER_LAUNCH")) per_launch = std::max<long long>(1, atoll(e));   // profiling sessions
             FNN_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned long long), st));
+            // FNN_CSW_ABORT_AFTER=<iterations>: measurement aid for sizes whose full solve does not fit a session - stop once
+            // that many CG iterations have run, report the rate, fail the call (the weights are NOT a solution)
+            static const long long abort_after = getenv("FNN_CSW_ABORT_AFTER") ? atoll(getenv("FNN_CSW_ABORT_AFTER")) : 0;
             while (true) {
                 FNN_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
                 FNN_CUDA(cudaStreamSynchronize(st));
                 if (h_sc->done) break;
+                if (abort_after > 0 && h_sc->iters_total >= abort_after) {
+                    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+                    fprintf(stderr, "[fnn] split weights n=%d aborted on request after %lld CG iterations in %lld CG solves, %.2f s since the solve began "
+                                    "(%.1f us per iteration all in)\n", n, (long long)h_sc->iters_total, (long long)cg_calls, secs,
+                            1e6 * secs / (double)h_sc->iters_total);
+                    fnn::set_error("split weights aborted after %lld CG iterations (FNN_CSW_ABORT_AFTER)", (long long)h_sc->iters_total);
+                    return FNN_E_STATE;
+                }
                 CgArgs a{x, r, p, w, y, Rw, P, RT, CT, T, T2, part1, part2, active, sc, bar, n, nchunks, (long long)np, (long long)nblk, per_launch, prof};
                 void* params[] = {&a};
                 FNN_CUDA(cudaLaunchCooperativeKernel(prof ? (const void*)k_cg_persistent<true> : (const void*)k_cg_persistent<false>, dim3((unsigned)persistent_grid), dim3(CGP_THREADS), params,
