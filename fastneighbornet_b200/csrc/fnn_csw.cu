@@ -1205,6 +1205,7 @@ struct Csw {
     cudaGraphExec_t cg_graph = nullptr;
     int64_t cg_calls = 0, outer = 0, inner = 0, launches = 0, launches_per_graph = 0;
     std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
+    double t_progress = 0.0;
     int persistent = 0;        // 1: k_cg_persistent (one cooperative launch per CG solve) instead of the graph path
     int persistent_grid = 0;
     unsigned long long* bar = nullptr;
@@ -1331,10 +1332,20 @@ struct Csw {
             // FNN_CSW_ABORT_AFTER=<iterations>: measurement aid for sizes whose full solve does not fit a session - stop once
             // that many CG iterations have run, report the rate, fail the call (the weights are NOT a solution)
             static const long long abort_after = getenv("FNN_CSW_ABORT_AFTER") ? atoll(getenv("FNN_CSW_ABORT_AFTER")) : 0;
+            static const double progress_every = getenv("FNN_CSW_PROGRESS") ? atof(getenv("FNN_CSW_PROGRESS")) : 0.0;   // seconds
             while (true) {
                 FNN_CUDA(cudaMemcpyAsync(h_sc, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
                 FNN_CUDA(cudaStreamSynchronize(st));
                 if (h_sc->done) break;
+                if (progress_every > 0.0) {
+                    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+                    if (secs - t_progress >= progress_every) {
+                        t_progress = secs;
+                        fprintf(stderr, "[fnn] split weights n=%d: %.0f s, %lld CG iterations, %lld CG solves, outer %lld, inner %lld\n", n, secs,
+                                (long long)h_sc->iters_total, (long long)cg_calls, (long long)outer, (long long)inner);
+                        fflush(stderr);
+                    }
+                }
                 if (abort_after > 0 && h_sc->iters_total >= abort_after) {
                     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
                     fprintf(stderr, "[fnn] split weights n=%d aborted on request after %lld CG iterations in %lld CG solves, %.2f s since the solve began "

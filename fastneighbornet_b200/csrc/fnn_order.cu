@@ -9,7 +9,7 @@
 // How this file does it (B200-first, not a translation):
 //   * The whole agglomeration state lives in HBM and the loop runs device-side: five kernels on the
 //     critical path of an iteration (scan, k_rx_stage, k_pick, k_rows, k_scatter) plus one on a forked
-//     graph branch (k_chain_patch, overlapped with the NEXT iteration's scan), no host round trip,
+//     graph branch (k_chain + k_patch, overlapped with the NEXT iteration's scan), no host round trip,
 //     replayed as a CUDA graph.  The host only expands the amalgamation log at the end (expandNodes
 //     stays on the host).
 //   * Physical layout != reference layout.  The live nodes occupy matrix slots [0,m):
@@ -24,7 +24,7 @@
 //     position, lower position), which is exactly "first strict minimum in (i, j<i) order".
 //   * Bit-exactness: compiled with --fmad=false.  u.Sx (a persistent left-to-right sum, :530-535) is
 //     reproduced bit for bit by the verified binade-collapsed summation of fnn_exact_sum.cuh, OFF the
-//     critical path: the next scan runs with the new cluster masked (Sx = -inf) while k_chain_patch
+//     critical path: the next scan runs with the new cluster masked (Sx = -inf) while k_chain + k_patch
 //     finishes u.Sx and evaluates the new cluster's 2 rows exactly; the two partial min-locs are merged by
 //     whichever finishes last.  The <=4 ComputeRx sums (:549-561) only feed the 4-candidate pick, so a
 //     parallel sum with a rigorous rounding bound decides it whenever the candidates are separated by
@@ -84,7 +84,7 @@ struct DevState {
     double alg_bytes;             // running sum of the selection scan's algorithmic bytes
     // ---- chain off the critical path: the cluster created by the previous iteration is masked in the scan
     int mask_su;                  // base slot of the cluster whose u.Sx is still being summed (-1: none)
-    unsigned int pad2;
+    unsigned int patch_ticket;    // k_patch: the last block to finish reduces the blocks' partial min-locs
     unsigned int commit_ticket;   // k_scatter: the last block to finish commits (m, c, P2, iter, done)
     int pad1;
     double scanQ, patchQ;         // partial min-locs: the masked scan / the new cluster's rows
@@ -209,7 +209,7 @@ __global__ void k_zero_diag(double* D, int64_t ld, int n) {
 // chain r.  Double-buffered so the staging of tile k+1 overlaps the dependent adds of tile k.
 constexpr int CH_TILE = 1024;
 constexpr size_t PICK_SMEM = sizeof(xsum::Smem) > 2 * 4 * CH_TILE * sizeof(double) ? sizeof(xsum::Smem) : 2 * 4 * CH_TILE * sizeof(double);
-// k_chain_patch: one chain.  When it fits, the whole staged chain is first copied into shared memory with every load in
+// k_chain + k_patch: one chain.  When it fits, the whole staged chain is first copied into shared memory with every load in
 // flight at once (one L2 round trip instead of one per pass / per opened segment of the exact summation).
 constexpr size_t CHAIN_SMEM_BASE = sizeof(xsum::SmemN<1>) > 2 * CH_TILE * sizeof(double) ? sizeof(xsum::SmemN<1>) : 2 * CH_TILE * sizeof(double);
 constexpr size_t CHAIN_SMEM_MAX = 220 * 1024;
@@ -274,7 +274,7 @@ __device__ __forceinline__ double duv_rule(bool uFirst, double dZX, double dYX, 
 // ------------------------------------------------------------------ K3a: selection result -> clusters
 // Computed redundantly by one thread of EVERY block of k_rx_stage (a handful of dependent L2 loads), so that it costs no
 // launch, no ticket and no fence: merge the partial min-locs - the masked scan's (single GPU) or every rank's, posted
-// into this rank's mailbox over NVLink (multi-GPU) - with k_chain_patch's partial for the masked cluster; then Cx, Cy from
+// into this rank's mailbox over NVLink (multi-GPU) - with k_chain + k_patch's partial for the masked cluster; then Cx, Cy from
 // the (i, j) key (or from the Relaxed/Random strategy) and the id-order swap of NetMakerOriginal.java:376-380.
 struct Sel { int cx, cxn, cy, cyn, need_rx, ok; double q; int i, j; };
 __device__ Sel select_decode(const int* __restrict__ id, const int* __restrict__ p2s, const DevState* st, const Mailbox* mail) {
@@ -302,7 +302,7 @@ __device__ Sel select_decode(const int* __restrict__ id, const int* __restrict__
                 if (better(q, key, bq, bk)) { bq = q; bk = key; }
             }
         }
-        // the cluster the scan had masked, evaluated exactly by k_chain_patch
+        // the cluster the scan had masked, evaluated exactly by k_chain + k_patch
         if (better(st->patchQ, st->patchKey, bq, bk)) { bq = st->patchQ; bk = st->patchKey; }
         r.q = bq; r.i = (int)(bk >> 32); r.j = (int)(bk & 0xffffffffu);
         cx = p2s[r.i]; cy = p2s[r.j];
@@ -715,7 +715,7 @@ k_rows(const double* __restrict__ D, int64_t ld, double* Sx, DevState* st, doubl
 
 // ------------------------------------------------------------------ K5b+K6a: scatter rows/cols + add sweep
 // The last block to finish commits the iteration (m, c, P2, iter, done) and masks the new cluster for the next scan:
-// its u.Sx is summed by k_chain_patch concurrently with that scan.
+// its u.Sx is summed by k_chain + k_patch concurrently with that scan.
 __global__ void __launch_bounds__(256)
 k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevState* st, const double* __restrict__ scratch,
           double* stage, const int* __restrict__ id, const int* __restrict__ p2s) {
@@ -778,24 +778,19 @@ k_scatter(double* D, int64_t ld, double* Sx, const int* __restrict__ pos, DevSta
 }
 
 // ------------------------------------------------------------------ K6b: u.Sx chain + the new cluster's pairs
-// Runs on a forked graph branch, concurrently with the NEXT iteration's selection scan (which reads the new cluster's Sx
-// as -inf).  (1) u.Sx = left-to-right sum of Dpu in position order (NetMakerOriginal.java:530-535), bit-exact;
-// (2) Q of (u-cluster, every other cluster) with that exact u.Sx, in the reference's role order (:215-226), min-loc on the
-// same (Q, i, j) key as the scan.  k_rx_stage (after the graph join) merges the two partial min-locs.
+// k_chain then k_patch run on a forked graph branch, concurrently with the NEXT iteration's selection scan (which reads the
+// new cluster's Sx as -inf).  (1) k_chain: u.Sx = left-to-right sum of Dpu in position order (NetMakerOriginal.java:530-535),
+// bit-exact; (2) k_patch: Q of (u-cluster, every other cluster) with that exact u.Sx, in the reference's role order
+// (:215-226), min-loc on the same (Q, i, j) key as the scan.  k_rx_stage (after the graph join) merges the two partial min-locs.
 __global__ void __launch_bounds__(PICK_THREADS, 1)
-k_chain_patch(const double* __restrict__ D, int64_t ld, double* Sx, const int* __restrict__ id, const int* __restrict__ pos,
-              const int* __restrict__ p2s, DevState* st, const double* __restrict__ stage, int serial_chain, int stage_cap) {
+k_chain(double* Sx, DevState* st, const double* __restrict__ stage, int serial_chain, int stage_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double (*buf)[1][CH_TILE] = reinterpret_cast<double (*)[1][CH_TILE]>(smem_raw);
     __shared__ double tot[1];
-    __shared__ Partial wbest[PICK_THREADS / 32];
     if (st->done) return;
     const int tid = threadIdx.x;
     const int su = st->mask_su;
-    const int m = st->m, P2 = st->P2;   // committed by k_scatter
-    const bool strategy = (st->mode != 0 && m > st->fallback);
-    double bq = INFINITY;
-    unsigned long long bk = ~0ull;
+    const int m = st->m;   // committed by k_scatter
     if (tid == 0) tl_stamp(st, TL_CHAIN0);
     if (su >= 0) {
         const int Ln = (m + xsum::THREADS - 1) / xsum::THREADS;
@@ -820,56 +815,97 @@ k_chain_patch(const double* __restrict__ D, int64_t ld, double* Sx, const int* _
         }
         const double Su = tot[0];
         if (tid == 0) { Sx[su] = Su; Sx[su + 1] = Su; tl_stamp(st, TL_CHAIN1); }
-        if (!strategy && !(m == 4 && st->c == 2)) {
-            const double cm2 = (double)st->c - 2.0;
-            const int posU = pos[su];
-            const double* ru = D + (int64_t)su * ld;
-            const double* run = ru + ld;
-            constexpr int PU = 4;   // 4 independent element groups per thread: all loads of a sweep are in flight together
-            for (int t0 = tid; t0 < m; t0 += PU * PICK_THREADS) {
-                double a[PU], b[PU], c2[PU], d2[PU], St[PU];
-                int pt[PU];
-                bool use[PU], pr[PU];
+    }
+}
+
+// (2) of the forked branch: Q of (new cluster, every other cluster) with the exact u.Sx k_chain has just written, in the
+// reference's role order, min-loc on the scan's key.  Small blocks (128 threads, no shared-memory ring) that co-reside with
+// the scan's CTAs, so that all loads of the 2*m entries are in flight at once even while the scan saturates HBM; the last
+// block to finish reduces the per-block partials into st->patchQ / patchKey.
+constexpr int PATCH_THREADS = 128;
+constexpr int PATCH_BLOCKS = 32;
+__global__ void __launch_bounds__(PATCH_THREADS)
+k_patch(const double* __restrict__ D, int64_t ld, const double* __restrict__ Sx, const int* __restrict__ pos, DevState* st,
+        Partial* __restrict__ ppart) {
+    if (st->done) return;
+    __shared__ Partial wbest[PATCH_THREADS / 32];
+    __shared__ bool amLast;
+    const int tid = threadIdx.x;
+    const int su = st->mask_su;
+    const int m = st->m, P2 = st->P2;
+    const bool strategy = (st->mode != 0 && m > st->fallback);
+    double bq = INFINITY;
+    unsigned long long bk = ~0ull;
+    if (su >= 0 && !strategy && !(m == 4 && st->c == 2)) {
+        const double Su = Sx[su];
+        const double cm2 = (double)st->c - 2.0;
+        const int posU = pos[su];
+        const double* ru = D + (int64_t)su * ld;
+        const double* run = ru + ld;
+        constexpr int PU = 4;   // 4 independent element groups per thread: all loads of a sweep are in flight together
+        const int stride = gridDim.x * PATCH_THREADS;
+        for (int t0 = blockIdx.x * PATCH_THREADS + tid; t0 < m; t0 += PU * stride) {
+            double a[PU], b[PU], c2[PU], d2[PU], St[PU];
+            int pt[PU];
+            bool use[PU], pr[PU];
 #pragma unroll
-                for (int u = 0; u < PU; ++u) {
-                    const int t = t0 + u * PICK_THREADS;
-                    pr[u] = t < P2;
-                    use[u] = t < m && !(pr[u] && (t & 1)) && (t & ~1) != su;   // representatives of the other clusters
-                    if (use[u]) {
-                        pt[u] = pos[t]; St[u] = Sx[t]; a[u] = ru[t]; b[u] = run[t];
-                        if (pr[u]) { c2[u] = ru[t + 1]; d2[u] = run[t + 1]; }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < PU; ++u) {
-                    if (!use[u]) continue;
-                    const bool uIsP = posU > pt[u];   // the higher position plays p (:208-213)
-                    double dpq;
-                    if (pr[u]) dpq = uIsP ? (((a[u] + c2[u]) + b[u]) + d2[u]) * 0.25 : (((a[u] + b[u]) + c2[u]) + d2[u]) * 0.25;
-                    else dpq = (a[u] + b[u]) * 0.5;
-                    const double q = uIsP ? (cm2 * dpq - Su) - St[u] : (cm2 * dpq - St[u]) - Su;
-                    const unsigned long long key = uIsP ? (((unsigned long long)posU << 32) | (unsigned)pt[u])
-                                                        : (((unsigned long long)pt[u] << 32) | (unsigned)posU);
-                    if (better(q, key, bq, bk)) { bq = q; bk = key; }
+            for (int u = 0; u < PU; ++u) {
+                const int t = t0 + u * stride;
+                pr[u] = t < P2;
+                use[u] = t < m && !(pr[u] && (t & 1)) && (t & ~1) != su;   // representatives of the other clusters
+                if (use[u]) {
+                    pt[u] = pos[t]; St[u] = Sx[t]; a[u] = ru[t]; b[u] = run[t];
+                    if (pr[u]) { c2[u] = ru[t + 1]; d2[u] = run[t + 1]; }
                 }
             }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double oq = __shfl_down_sync(0xffffffffu, bq, off);
-                const unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, off);
-                if (better(oq, ok, bq, bk)) { bq = oq; bk = ok; }
+            for (int u = 0; u < PU; ++u) {
+                if (!use[u]) continue;
+                const bool uIsP = posU > pt[u];   // the higher position plays p (:208-213)
+                double dpq;
+                if (pr[u]) dpq = uIsP ? (((a[u] + c2[u]) + b[u]) + d2[u]) * 0.25 : (((a[u] + b[u]) + c2[u]) + d2[u]) * 0.25;
+                else dpq = (a[u] + b[u]) * 0.5;
+                const double q = uIsP ? (cm2 * dpq - Su) - St[u] : (cm2 * dpq - St[u]) - Su;
+                const unsigned long long key = uIsP ? (((unsigned long long)posU << 32) | (unsigned)pt[u])
+                                                    : (((unsigned long long)pt[u] << 32) | (unsigned)posU);
+                if (better(q, key, bq, bk)) { bq = q; bk = key; }
             }
-            if ((tid & 31) == 0) wbest[tid >> 5] = Partial{bq, bk};
-            __syncthreads();
-            if (tid == 0)
-                for (int w = 1; w < PICK_THREADS / 32; ++w)
-                    if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
         }
     }
+    auto warp_min = [&]() {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double oq = __shfl_down_sync(0xffffffffu, bq, off);
+            const unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, off);
+            if (better(oq, ok, bq, bk)) { bq = oq; bk = ok; }
+        }
+    };
+    warp_min();
+    if ((tid & 31) == 0) wbest[tid >> 5] = Partial{bq, bk};
+    __syncthreads();
     if (tid == 0) {
-        st->patchQ = bq;
-        st->patchKey = bk;
-        tl_stamp(st, TL_PATCH1);
+        for (int w = 1; w < PATCH_THREADS / 32; ++w)
+            if (better(wbest[w].q, wbest[w].key, bq, bk)) { bq = wbest[w].q; bk = wbest[w].key; }
+        ppart[blockIdx.x] = Partial{bq, bk};
+        __threadfence();
+        amLast = (atomicAdd(&st->patch_ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (amLast && tid < 32) {
+        __threadfence();
+        bq = INFINITY; bk = ~0ull;
+        for (int b = tid; b < (int)gridDim.x; b += 32) {
+            const double pq = __ldcg(&ppart[b].q);
+            const unsigned long long pk = __ldcg(&ppart[b].key);
+            if (better(pq, pk, bq, bk)) { bq = pq; bk = pk; }
+        }
+        warp_min();
+        if (tid == 0) {
+            st->patchQ = bq;
+            st->patchKey = bk;
+            st->patch_ticket = 0;
+            tl_stamp(st, TL_PATCH1);
+        }
     }
 }
 
@@ -913,16 +949,17 @@ struct fnn_ctx {
     DevState* st = nullptr;
     Partial* partials = nullptr;
     double* rx_part = nullptr;        // per-block partial ComputeRx sums of k_rx_stage
+    Partial* patch_part = nullptr;    // per-block partial min-locs of k_patch
     int scan_grid = 0, row_grid = 0;
     // u.Sx chain + new-cluster patch on a forked branch, concurrent with the next scan (which then leaves one SM to it)
-    size_t chain_smem = 0;            // k_chain_patch: exact-summation workspace + (if it fits) the staged chain
+    size_t chain_smem = 0;            // k_chain + k_patch: exact-summation workspace + (if it fits) the staged chain
     int chain_stage_cap = 0;          // elements of the chain that fit in shared memory (0: read from global)
     bool overlap = false;
     int force_exact = 0;              // A/B: always decide the pick with the exact left-to-right sums
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool join_pending = false;        // a k_chain_patch has been issued on stream2 and not yet waited for
-    int launches_per_iter() const { return 6 + (o.mode >= FNN_RANDOM_N ? 2 : 0) + (o.mode == FNN_RELAXED ? 1 : 0); }
+    bool join_pending = false;        // a k_chain + k_patch has been issued on stream2 and not yet waited for
+    int launches_per_iter() const { return 7 + (o.mode >= FNN_RANDOM_N ? 2 : 0) + (o.mode == FNN_RELAXED ? 1 : 0); }
     DevState* h_st = nullptr;  // pinned
     CUtensorMap tmap;
     bool have_tmap = false;
@@ -988,7 +1025,7 @@ extern "C" void fnn_ctx_destroy(fnn_ctx* c) {
     cudaFree(c->mail); cudaFree(c->peers);
     cudaFree(c->nbrpos); cudaFree(c->pairs); cudaFree(c->walk); cudaFree(c->walk_ticket);
     cudaFree(c->id); cudaFree(c->pos); cudaFree(c->p2s); cudaFree(c->amalg); cudaFree(c->st); cudaFree(c->partials);
-    cudaFree(c->rx_part); cudaFree(c->tl);
+    cudaFree(c->rx_part); cudaFree(c->patch_part); cudaFree(c->tl);
     if (c->h_st) cudaFreeHost(c->h_st);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1058,6 +1095,7 @@ static int ctx_build(fnn_ctx* c, const fnn_opts* o, int64_t n) {
     c->row_grid = std::max<int>(1, std::min<int64_t>((n + 255) / 256, std::min(c->sms * 4, RX_BLOCKS_MAX)));
     FNN_ALLOC(c->partials, sizeof(Partial) * c->sms);
     FNN_ALLOC(c->rx_part, sizeof(double) * 8 * RX_BLOCKS_MAX);
+    FNN_ALLOC(c->patch_part, sizeof(Partial) * PATCH_BLOCKS);
     if (o->record_trace) FNN_ALLOC(c->trace, sizeof(double) * 8 * (n + 8));
     if (o->mode == FNN_RELAXED) {
         c->rl_max_lists = (int)(2 * n + 16); c->rl_tie_cap = (int)(16 * n + 65536); c->rl_mymin_cap = (int)(8 * n + 65536);
@@ -1098,7 +1136,7 @@ static int ctx_build(fnn_ctx* c, const fnn_opts* o, int64_t n) {
         const size_t want = CHAIN_SMEM_BASE + sizeof(double) * (size_t)c->rxs_ld;
         if (want <= CHAIN_SMEM_MAX) { c->chain_smem = want; c->chain_stage_cap = (int)c->rxs_ld; }
         else { c->chain_smem = CHAIN_SMEM_BASE; c->chain_stage_cap = 0; }
-        FNN_CUDA(cudaFuncSetAttribute(k_chain_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
+        FNN_CUDA(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
     }
     int trc = make_tensor_map(c);
     if (trc) return trc;
@@ -1202,7 +1240,7 @@ static int make_tensor_map(fnn_ctx* c) {
     c->have_tmap = true;
     return FNN_OK;
 }
-// everything of an iteration after the scan.  The previous iteration's k_chain_patch (forked branch) joins here: the
+// everything of an iteration after the scan.  The previous iteration's k_chain + k_patch (forked branch) joins here: the
 // strategy kernels, the selection merge and the update all need the new cluster's exact Sx.
 static inline void launch_rest(fnn_ctx* c) {
     if (c->join_pending) { cudaStreamWaitEvent(c->stream, c->ev_join, 0); c->join_pending = false; }
@@ -1225,8 +1263,8 @@ static inline void launch_rest(fnn_ctx* c) {
         cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
         cs = c->stream2;
     }
-    k_chain_patch<<<1, PICK_THREADS, c->chain_smem, cs>>>(c->D, c->ld, c->Sx, c->id, c->pos, c->p2s, c->st, c->stage, c->serial_chain,
-                                                         c->chain_stage_cap);
+    k_chain<<<1, PICK_THREADS, c->chain_smem, cs>>>(c->Sx, c->st, c->stage, c->serial_chain, c->chain_stage_cap);
+    k_patch<<<PATCH_BLOCKS, PATCH_THREADS, 0, cs>>>(c->D, c->ld, c->Sx, c->pos, c->st, c->patch_part);
     if (c->overlap) { cudaEventRecord(c->ev_join, c->stream2); c->join_pending = true; }
 }
 // the forked branch has to be back on the main stream before a capture ends, before the state is read, before the next run
