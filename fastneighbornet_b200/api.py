@@ -189,6 +189,15 @@ class Context:
         assert D.shape == (self.n, self.n)
         _check(lib().fnn_ctx_load_host(self._h, _dp(D)))
 
+    def load_host_rows(self, D_rows, row0):
+        """Upload rows [row0, row0 + len(D_rows)) only (fnn_ctx_load_host_rows); finish with commit_load()."""
+        D_rows = np.ascontiguousarray(D_rows, dtype=np.float64)
+        assert D_rows.ndim == 2 and D_rows.shape[1] == self.n
+        _check(lib().fnn_ctx_load_host_rows(self._h, _dp(D_rows), int(row0), D_rows.shape[0]))
+
+    def commit_load(self):
+        _check(lib().fnn_ctx_commit_load(self._h))
+
     def load_host_sharded(self, D):
         """N>1 (torch.distributed initialised, contexts wired): every rank uploads 1/world of the rows over its own PCIe
         link, the row blocks then travel between the GPUs over NVLink (NCCL broadcast on the library's device matrix) -

@@ -117,7 +117,11 @@ int fnn_ctx_matrix_ptr(fnn_ctx* c, double** dptr, int64_t* ld);
  * (Q,i,j) partial min-locs are exchanged through peer-mapped mailboxes over NVLink inside the kernels.
  * State and matrix are replicated (every rank loads the same matrix and returns the same ordering).
  * fnn_ctx_ipc_handle writes this rank's 64-byte CUDA IPC handle; the host layer all-gathers the handles
- * (torch.distributed / MPI / files) and passes the world*64 bytes, rank-ordered, to fnn_ctx_connect. */
+ * (torch.distributed / MPI / files) and passes the world*64 bytes, rank-ordered, to fnn_ctx_connect.
+ * Every rank must call fnn_ctx_order the same number of times on a wired context (the mailbox tags carry a per-context run
+ * counter).  A peer that never posts (it failed, or skipped the call) does not hang the others: after 30 s of waiting inside
+ * the kernel they stop with FNN_E_STATE (device-side code 30).  A context may be destroyed as soon as its own fnn_ctx_order
+ * has returned: the last exchange of a run completes on every rank before any rank can finish. */
 int fnn_ctx_ipc_handle(fnn_ctx* c, void* handle_out /* 64 bytes */);
 int fnn_ctx_connect(fnn_ctx* c, int32_t rank, int32_t world, const void* handles /* world * 64 bytes */);
 

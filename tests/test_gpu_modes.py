@@ -45,6 +45,12 @@ def test_modes_default_fallback_n1500(fnn, mode):
     _check(fnn, tree_matrix(1500, 4, 0.05), mode, seed=12345, fallback=1024)
 
 
+def test_relaxed_n6000_trace_exact(fnn):
+    """A size at which the Relaxed strategy runs for ~5 000 iterations (m > 1024) with rows of thousands of candidates:
+    batched row scans, tie lists, the strategy-only graph and the hand-over to the canonical tail - trace-exact."""
+    _check(fnn, tree_matrix(6000, 9, 0.05), "relaxed", seed=4242, fallback=1024)
+
+
 def test_random_mult(fnn):
     _check(fnn, tree_matrix(200, 2, 0.05), "random_nlogn", seed=9, mult=2)
 

@@ -88,6 +88,20 @@ def test_certified_pick_statistics(fnn):
     assert st2["picks_exact"] > 0 and st2["picks_certified"] == 0
 
 
+def test_row_block_upload_equals_whole_upload(fnn):
+    """fnn_ctx_load_host_rows + fnn_ctx_commit_load (the per-rank upload of the N>1 path) on one GPU: three row blocks in
+    arbitrary order give the ordering of a whole-matrix upload."""
+    D = tree_matrix(777, 6, 0.05)
+    with fnn.Context(777) as c:
+        c.load_host(D)
+        o_ref = c.order()
+        for r0, r1 in ((500, 777), (0, 123), (123, 500)):
+            c.load_host_rows(D[r0:r1], r0)
+        c.commit_load()
+        o = c.order()
+    assert (o == o_ref).all()
+
+
 def test_rowsums(fnn):
     D = tree_matrix(777, 5)
     assert (fnn.rowsums(D) == oracle.rowsums(D)).all()
