@@ -453,6 +453,15 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
     // value, and the certified decision is then cross-checked against it), the exact sums decide.
     const bool need_rx = (Cxn >= 0 || Cyn >= 0);
     if (need_rx) {
+        // the control thread's four candidate distances are requested before the reduction below, not after it
+        double dcand[4] = {0.0, 0.0, 0.0, 0.0};
+        if (tid == 0) {
+            const int zs4[4] = {Cx, Cxn, Cy, Cyn};
+            const int ra[4] = {0, 1, 0, 1}, rb[4] = {2, 2, 3, 3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (zs4[ra[k]] >= 0 && zs4[rb[k]] >= 0) dcand[k] = D[(int64_t)zs4[ra[k]] * ld + zs4[rb[k]]];
+        }
         if (tid < 256) {   // warp w sums quantity w over the blocks
             const int q = tid >> 5, lane = tid & 31;
             double v = 0.0;
@@ -465,7 +474,6 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
         if (tid == 0) {
             const double U = 1.1102230246251565e-16;
             const double f = (double)(c + (Cxn >= 0) + (Cyn >= 0)) - 2.0;
-            const int zs4[4] = {Cx, Cxn, Cy, Cyn};
             const int ra[4] = {0, 1, 0, 1}, rb[4] = {2, 2, 3, 3};
             double Q[4], e[4];
             bool pres[4] = {true, Cxn >= 0, Cyn >= 0, Cxn >= 0 && Cyn >= 0};
@@ -475,7 +483,7 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
                 if (!pres[k]) continue;
                 const double Ra = rxa[ra[k]], Rb = rxa[rb[k]];
                 const double Ea = rxa[4 + ra[k]] * ((2.0 * (double)m + 256.0) * U), Eb = rxa[4 + rb[k]] * ((2.0 * (double)m + 256.0) * U);
-                const double t = f * D[(int64_t)zs4[ra[k]] * ld + zs4[rb[k]]];
+                const double t = f * dcand[k];
                 Q[k] = (t - Ra) - Rb;
                 e[k] = 1.01 * (Ea + Eb) + 8.0 * U * (fabs(t) + fabs(Ra) + fabs(Rb));
                 finite = finite && isfinite(Q[k]) && isfinite(e[k]);
@@ -512,7 +520,7 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
         const int ks = s_kstar;
         x = (ks & 1) ? Cxn : Cx;
         y = (ks & 2) ? Cyn : Cy;
-        st->cert_ok += 1;
+        atomicAdd((unsigned long long*)&st->cert_ok, 1ull);   // result unused: no round trip
     } else {
         int mm = c + (Cxn >= 0) + (Cyn >= 0);
         const double f = (double)mm - 2.0;
@@ -523,9 +531,9 @@ k_pick(double* D, int64_t ld, double* Sx, int* id, int* pos, int* p2s, DevState*
         if (Cxn >= 0 && Cyn >= 0) { double q = (f * d(Cxn, Cyn) - rx[1]) - rx[3]; if (q < best) { x = Cxn; y = Cyn; best = q; kx = 3; } }
         if (need_rx) {
             if (s_kstar >= 0) {   // exact sums were computed although the pick was certifiable: cross-check the certificate
-                st->cert_ok += 1;
+                atomicAdd((unsigned long long*)&st->cert_ok, 1ull);
                 if (s_kstar != kx) { st->error = 21; st->done = 1; st->skip = 1; return; }
-            } else st->cert_fail += 1;
+            } else atomicAdd((unsigned long long*)&st->cert_fail, 1ull);
         }
         if (trace) {
             double* tr = trace + 8 * (int64_t)st->iter;
