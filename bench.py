@@ -458,6 +458,14 @@ def main():
                         "alg_bytes_per_cg_iteration": 112.0 * npairs, "achieved": 112.0 * npairs / (us_it * 1e-6) / 1e9, "unit": "GB/s",
                         "frac": 112.0 * npairs / (us_it * 1e-6) / 1e9 / peak, "gpu_launches": stc["kernel_launches"], "kept_splits": int((xc > 1e-6).sum()),
                         "bound": "barrier/L2 latency at this size (8 grid barriers per iteration, DESIGN.md 4.3), HBM only above n ~ 3000"})
+        # the full-size configs[1] run (5000 taxa: 52 minutes) does not fit a bench step; its committed record rides along
+        full = os.path.join(ROOT, "profiles", "r2_config1_n5000.json")
+        if os.path.exists(full):
+            try:
+                with open(full) as f_:
+                    configs[-1]["full_size_builder_run"] = dict(json.load(f_), source="profiles/r2_config1_n5000.json (tools/config1_run.py 5000, not re-run here)")
+            except Exception:
+                pass
         fnn.release_cache()
         configs.append(timed("configs[2] without -additive: Relaxed, 20000 taxa (row scans: SURVEY 8d K7 bytes + the canonical tail's scan bytes)",
                              20000, 3, 0.05, "strategy_alg_bytes", mode="relaxed", seed=7))
