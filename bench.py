@@ -409,7 +409,11 @@ def main():
         if os.path.exists(tfile):
             try:
                 with open(tfile) as f:
-                    roofline["traffic"] = json.load(f).get("traffic_bytes_per_launch")
+                    tj = json.load(f)
+                roofline["traffic"] = tj.get("traffic_bytes_per_launch")
+                # the ncu capture is of the first launches (m ~ n): compare it with THAT launch's algorithmic bytes
+                roofline["traffic_launch_alg_bytes"] = tj.get("alg_bytes_same_launch")
+                roofline["traffic_source"] = tj.get("source")
             except Exception:
                 pass
     del pristine
