@@ -8,7 +8,7 @@
 //
 // How this file does it (B200-first, not a translation):
 //   * The whole agglomeration state lives in HBM and the loop runs device-side: five kernels on the
-//     critical path of an iteration (scan, k_rx_stage, k_pick, k_rows, k_scatter) plus one on a forked
+//     critical path of an iteration (scan, k_rx_stage, k_pick, k_rows, k_scatter) plus two on a forked
 //     graph branch (k_chain + k_patch, overlapped with the NEXT iteration's scan), no host round trip,
 //     replayed as a CUDA graph.  The host only expands the amalgamation log at the end (expandNodes
 //     stays on the host).

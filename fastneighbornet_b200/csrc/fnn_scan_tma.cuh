@@ -189,7 +189,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
     const double cm2 = (double)st->c - 2.0;
     const int tid = threadIdx.x;
     const int ew = effective_world(st->world, m);   // ranks that share this scan (1: every rank scans all tiles)
-    // the cluster created by the previous iteration: its u.Sx is still being summed by k_chain_patch on a forked
+    // the cluster created by the previous iteration: its u.Sx is still being summed by k_chain on a forked
     // branch, which also evaluates that cluster's pairs exactly; here its Sx reads as -inf, i.e. Q = +inf
     const int msk = st->mask_su;
 
@@ -375,7 +375,7 @@ k_scan_tma(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ 
                 __threadfence_system();
                 for (int r = 0; r < st->world; ++r) mail_store_tag(&peers->box[r]->slot[par][st->rank], tag);
             } else {
-                // merged with k_chain_patch's partial (the masked cluster) and decoded by k_rx_stage
+                // merged with k_patch's partial (the masked cluster) and decoded by k_rx_stage
                 st->scanQ = bq;
                 st->scanKey = bk;
             }
