@@ -1,10 +1,11 @@
-"""CPU models of the three non-obvious device algorithms, held to brute force on adversarial inputs.  They mirror the
+"""CPU models of the non-obvious device algorithms, held to brute force on adversarial inputs.  They mirror the
 kernels' logic step by step (same windows, same summaries, same checks), so the reasoning that makes the GPU results
 bit-exact is exercised on every CPU run, far beyond what the GPU parity tests happen to hit:
 
   * the collapsed exact left-to-right summation            (csrc/fnn_exact_sum.cuh)
   * the speculative parallel java.util.Random walk          (csrc/fnn_modes.cuh: k_random_walk)
   * the slack of the selection scan's filter-then-verify    (csrc/fnn_scan_tma.cuh: delta)
+  * the certificate of the 4-candidate pick                 (csrc/fnn_order.cu: k_pick)
 """
 import math
 import struct
@@ -340,3 +341,101 @@ def test_scan_filter_slack_bounds_the_rounding_difference():
             worst = max(worst, abs(approx - q) / delta)
             assert abs(approx - q) <= delta, (trial, kind, approx, q, delta)
     assert worst < 0.5   # the bound has slack to spare
+
+
+# ------------------------------------------------------------------ certified 4-candidate pick model (csrc/fnn_order.cu: k_pick)
+U53 = 2.0 ** -53
+
+
+def _seq_sum(a):
+    s = 0.0
+    for v in a:
+        s += float(v)
+    return s
+
+
+def _certificate(m, f, d, terms, present):
+    """Mirror of k_pick's certificate.  terms[r] = the m weighted ComputeRx terms of chain r (r = Cx, Cx.nbr, Cy, Cy.nbr);
+    the kernel sums them in SOME order (here: numpy's pairwise sum of a random permutation) and bounds the difference to
+    the reference's left-to-right sum.  Returns (kstar or None, exact pick)."""
+    ra, rb = (0, 1, 0, 1), (2, 2, 3, 3)
+    rng = np.random.default_rng(len(terms[0]) + int(abs(f)))
+    R = [float(np.sum(rng.permutation(t))) for t in terms]
+    A = [float(np.sum(np.abs(t))) for t in terms]
+    E = [a * ((2.0 * m + 256.0) * U53) for a in A]
+    Q, e, ks = {}, {}, None
+    for k in range(4):
+        if not present[k]:
+            continue
+        t = f * d[k]
+        Q[k] = (t - R[ra[k]]) - R[rb[k]]
+        e[k] = 1.01 * (E[ra[k]] + E[rb[k]]) + 8.0 * U53 * (abs(t) + abs(R[ra[k]]) + abs(R[rb[k]]))
+        if ks is None or Q[k] < Q[ks]:
+            ks = k
+    cert = all(math.isfinite(Q[k]) and math.isfinite(e[k]) for k in Q)
+    cert = cert and all(k == ks or Q[ks] + e[ks] < Q[k] - e[k] for k in Q)
+    # the reference: left-to-right sums, strict '<' in candidate order (NetMakerOriginal.java:428-452)
+    X = [_seq_sum(t) for t in terms]
+    best, kx = (f * d[0] - X[0]) - X[2], 0
+    for k in (1, 2, 3):
+        if present[k]:
+            q = (f * d[k] - X[ra[k]]) - X[rb[k]]
+            if q < best:
+                best, kx = q, k
+    return (ks if cert else None), kx
+
+
+def test_summation_order_bound_of_the_certificate():
+    """|left-to-right sum - any other order| <= (2m+256) * 2^-53 * sum|a| : the E of the certificate, on adversarial inputs
+    (wide magnitude ranges, alternating signs, sorted either way)."""
+    rng = np.random.default_rng(5)
+    for m in (7, 100, 3001, 20000):
+        for kind in range(6):
+            a = rng.random(m)
+            if kind == 1:
+                a = a * 10.0 ** rng.integers(-8, 8, m)
+            elif kind == 2:
+                a = np.sort(a * 10.0 ** rng.integers(-6, 6, m))
+            elif kind == 3:
+                a = np.sort(a * 10.0 ** rng.integers(-6, 6, m))[::-1]
+            elif kind == 4:
+                a = a * np.where(rng.random(m) < 0.5, -1.0, 1.0) * 10.0 ** rng.integers(-3, 3, m)
+            elif kind == 5:
+                a = np.concatenate([[1e16], rng.random(m - 1)])
+            seq = _seq_sum(a)
+            bound = (2.0 * m + 256.0) * U53 * float(np.sum(np.abs(a)))
+            for other in (float(np.sum(a)), float(np.sum(a[::-1])), float(np.sum(rng.permutation(a))), math.fsum(a),
+                          _seq_sum(a[::-1])):
+                assert abs(seq - other) <= bound, (m, kind, seq, other, bound)
+
+
+def test_certified_pick_never_disagrees_with_the_exact_sums():
+    """Whenever the certificate accepts, the candidate it names is the one the reference's exact left-to-right sums pick;
+    on exact ties and near-ties it must refuse.  Random, tie and near-tie instances."""
+    rng = np.random.default_rng(11)
+    accepted = refused = 0
+    for trial in range(400):
+        m = int(rng.integers(5, 4000))
+        f = float(m // 2)
+        mode = trial % 4
+        base = rng.random((4, m)) + 0.1
+        if mode == 1:      # exact ties: identical chains and distances (integer-like data)
+            base = np.tile(np.round(base[0] * 4.0), (4, 1))
+        elif mode == 2:    # near-ties: chains that differ in one ulp-sized term
+            base = np.tile(base[0], (4, 1))
+            base[1, 0] = np.nextafter(base[1, 0], 2.0)
+            base[3, -1] = np.nextafter(base[3, -1], 0.0)
+        w = np.where(rng.random(m) < 0.5, 1.0, 0.5)
+        terms = [base[r] * w for r in range(4)]
+        d = rng.random(4) if mode in (0, 3) else np.full(4, 0.5)
+        present = (True, bool(rng.integers(0, 2)) or mode != 0, bool(rng.integers(0, 2)) or mode != 0, False)
+        present = present[:3] + (present[1] and present[2],)
+        ks, kx = _certificate(m, f, d, terms, present)
+        if ks is None:
+            refused += 1
+        else:
+            accepted += 1
+            assert ks == kx, (trial, mode, ks, kx)
+        if mode == 1 and sum(present) > 1:
+            assert ks is None   # exact ties are never certified
+    assert accepted > 100 and refused > 100
