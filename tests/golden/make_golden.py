@@ -38,6 +38,22 @@ def main():
     with open(os.path.join(HERE, "order_golden.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", len(out), "cases")
+    # split weights: both parity-ladder levels (L0 = the reference's order, L1 = the production formulation), frozen
+    from fastneighbornet_b200 import synth
+    csw = []
+    for n, seed, eps in ((8, 1, 0.05), (14, 2, 0.05), (24, 6, 0.05), (40, 2, 0.05), (60, 3, 0.2)):
+        D = tree_matrix(n, seed, eps)
+        o, _, _ = oracle.order(D)
+        d_pos = oracle.setup_d(o, synth.upper_triangle(D))
+        x0, s0 = oracle.split_weights(n, d_pos)
+        x1, s1 = oracle.l1_split_weights(n, d_pos)
+        csw.append({"n": n, "seed": seed, "eps": eps, "d_pos_sha256": hashlib.sha256(d_pos.tobytes()).hexdigest(),
+                    "l0_sha256": hashlib.sha256(x0.tobytes()).hexdigest(), "l0_cg_iters": s0["cg_iters"], "l0_kept": int((x0 > 1e-6).sum()),
+                    "l1_sha256": hashlib.sha256(x1.tobytes()).hexdigest(), "l1_cg_iters": s1["cg_iters"], "l1_kept": int((x1 > 1e-6).sum()),
+                    "l0_weights": x0.tolist() if n <= 14 else None})
+    with open(os.path.join(HERE, "csw_golden.json"), "w") as f:
+        json.dump(csw, f, indent=1)
+    print("wrote", len(csw), "split-weight cases")
 
 
 if __name__ == "__main__":

@@ -111,6 +111,27 @@ def test_persistent_kernel_equals_graph_path_n300(fnn):
     assert sa["kernel_launches"] < sb["kernel_launches"] / 50
 
 
+def test_split_weights_match_committed_golden_fixtures(fnn):
+    """tests/golden/csw_golden.json (generated by tests/golden/make_golden.py from the oracle): the production path must
+    reproduce the frozen L1 weights and the literal-order path the frozen L0 weights, bit for bit, without the oracle in
+    the loop."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "csw_golden.json")) as f:
+        cases = json.load(f)
+    for g in cases:
+        D = tree_matrix(g["n"], g["seed"], g["eps"])
+        o = fnn.order(D)
+        du = synth.upper_triangle(D)
+        x1, s1 = fnn.split_weights(o, du)
+        x0, s0 = fnn.split_weights(o, du, variant="literal")
+        assert hashlib.sha256(x1.tobytes()).hexdigest() == g["l1_sha256"] and s1["cg_iters"] == g["l1_cg_iters"]
+        assert hashlib.sha256(x0.tobytes()).hexdigest() == g["l0_sha256"] and s0["cg_iters"] == g["l0_cg_iters"]
+        if g["l0_weights"] is not None:
+            assert x0.tolist() == g["l0_weights"]
+
+
 def test_additive_tree_needs_no_iterations(fnn):
     """eps = 0: the unconstrained optimum is feasible up to rounding; weights reproduce the tree."""
     D, o, du = _problem(30, 5, 0.0)

@@ -148,6 +148,28 @@ def test_golden_fixtures():
         assert hashlib.sha256(tr.tobytes()).hexdigest() == c["trace_sha256"]
 
 
+def test_golden_split_weight_fixtures():
+    """tests/golden/csw_golden.json freezes both levels of the split-weight parity ladder (L0 = the reference's own
+    operation order, L1 = the production formulation): weights bit for bit, CG iteration counts, kept-split counts."""
+    import hashlib
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "csw_golden.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 5
+    for g in cases:
+        D = tree_matrix(g["n"], g["seed"], g["eps"])
+        o, _, _ = oracle.order(D)
+        d_pos = oracle.setup_d(o, synth.upper_triangle(D))
+        assert hashlib.sha256(d_pos.tobytes()).hexdigest() == g["d_pos_sha256"]
+        x0, s0 = oracle.split_weights(g["n"], d_pos)
+        x1, s1 = oracle.l1_split_weights(g["n"], d_pos)
+        assert hashlib.sha256(x0.tobytes()).hexdigest() == g["l0_sha256"] and s0["cg_iters"] == g["l0_cg_iters"]
+        assert hashlib.sha256(x1.tobytes()).hexdigest() == g["l1_sha256"] and s1["cg_iters"] == g["l1_cg_iters"]
+        assert int((x0 > 1e-6).sum()) == g["l0_kept"] and int((x1 > 1e-6).sum()) == g["l1_kept"]
+        if g["l0_weights"] is not None:
+            assert x0.tolist() == g["l0_weights"]
+
+
 def test_small_n_identity():
     for n in (1, 2, 3):
         o, _, _ = oracle.order(np.zeros((n, n)))
