@@ -102,6 +102,25 @@ def test_row_block_upload_equals_whole_upload(fnn):
     assert (o == o_ref).all()
 
 
+def test_orderings_match_committed_golden_fixtures(fnn):
+    """tests/golden/order_golden.json (tests/golden/make_golden.py): orderings and per-iteration traces frozen as hashes -
+    the CUDA path against the committed vectors, without the oracle in the loop."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "order_golden.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 7
+    for g in cases:
+        D = tree_matrix(g["n"], g["seed"], g["eps"]) if g["kind"] == "tree" else integer_matrix(g["n"], g["seed"])
+        assert hashlib.sha256(D.tobytes()).hexdigest() == g["input_sha256"]
+        o, tr, _ = _run_gpu(fnn, D)
+        assert hashlib.sha256(o.astype(np.int32).tobytes()).hexdigest() == g["ordering_sha256"]
+        assert hashlib.sha256(np.ascontiguousarray(tr).tobytes()).hexdigest() == g["trace_sha256"] and tr.shape[0] == g["iterations"]
+        if g["ordering"] is not None:
+            assert o.tolist() == g["ordering"]
+
+
 def test_rowsums(fnn):
     D = tree_matrix(777, 5)
     assert (fnn.rowsums(D) == oracle.rowsums(D)).all()
